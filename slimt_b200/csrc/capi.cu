@@ -1,0 +1,249 @@
+// extern "C" surface declared in include/slimt_b200.h.
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/slimt_b200.h"
+#include "engine.cuh"
+#include "service.cuh"
+
+struct slimt_b200_ctx {
+  sb::Context c;
+};
+struct slimt_b200_model {
+  sb::Model m;
+};
+
+extern "C" {
+
+const char* slimt_b200_last_error(void) { return sb::last_error(); }
+const char* slimt_b200_version(void) { return "slimt_b200 0.1 (sm_100a, tcgen05 kind::i8)"; }
+
+int slimt_b200_ctx_create(int device, slimt_b200_ctx** out) {
+  auto* ctx = new (std::nothrow) slimt_b200_ctx();
+  if (!ctx) return 1;
+  if (ctx->c.init(device)) {
+    delete ctx;
+    return 1;
+  }
+  *out = ctx;
+  return 0;
+}
+
+void slimt_b200_ctx_destroy(slimt_b200_ctx* ctx) {
+  if (!ctx) return;
+  ctx->c.destroy();
+  delete ctx;
+}
+
+int slimt_b200_ctx_synchronize(slimt_b200_ctx* ctx) {
+  SB_CUDA(cudaSetDevice(ctx->c.device));
+  SB_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  return 0;
+}
+
+void* slimt_b200_dev_alloc(slimt_b200_ctx* ctx, size_t bytes) {
+  cudaSetDevice(ctx->c.device);
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    sb::set_error("cudaMalloc failed for " + std::to_string(bytes) + " bytes");
+    return nullptr;
+  }
+  return p;
+}
+void slimt_b200_dev_free(slimt_b200_ctx* ctx, void* p) {
+  cudaSetDevice(ctx->c.device);
+  cudaFree(p);
+}
+int slimt_b200_memcpy_h2d(slimt_b200_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  SB_CUDA(cudaSetDevice(ctx->c.device));
+  SB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->c.stream));
+  SB_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  ctx->c.h2d_bytes += bytes;
+  return 0;
+}
+int slimt_b200_memcpy_d2h(slimt_b200_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  SB_CUDA(cudaSetDevice(ctx->c.device));
+  SB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->c.stream));
+  SB_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  ctx->c.d2h_bytes += bytes;
+  return 0;
+}
+int slimt_b200_timer_start(slimt_b200_ctx* ctx) {
+  SB_CUDA(cudaSetDevice(ctx->c.device));
+  SB_CUDA(cudaEventRecord(ctx->c.ev0, ctx->c.stream));
+  return 0;
+}
+int slimt_b200_timer_stop(slimt_b200_ctx* ctx, double* ms) {
+  SB_CUDA(cudaSetDevice(ctx->c.device));
+  SB_CUDA(cudaEventRecord(ctx->c.ev1, ctx->c.stream));
+  SB_CUDA(cudaEventSynchronize(ctx->c.ev1));
+  float t = 0;
+  SB_CUDA(cudaEventElapsedTime(&t, ctx->c.ev0, ctx->c.ev1));
+  *ms = t;
+  return 0;
+}
+int slimt_b200_flush_l2(slimt_b200_ctx* ctx, size_t bytes) {
+  sb::Context& c = ctx->c;
+  SB_CUDA(cudaSetDevice(c.device));
+  if (bytes > c.flush_bytes) {
+    if (c.flush_buf) SB_CUDA(cudaFree(c.flush_buf));
+    c.flush_buf = nullptr;
+    SB_CUDA(cudaMalloc(&c.flush_buf, bytes));
+    c.flush_bytes = bytes;
+  }
+  SB_CUDA(cudaMemsetAsync(c.flush_buf, 1, bytes, c.stream));
+  return 0;
+}
+
+void slimt_b200_qmm_prepare_weight_quantized_transposed(const int8_t* input, int8_t* output, size_t rows, size_t cols) {
+  // Already B^T row-major [cols][rows]: tcgen05 consumes it as a K-major operand unchanged.
+  memcpy(output, input, rows * cols);
+}
+
+void slimt_b200_qmm_prepare_weight_transposed(const float* weights, int8_t* prepared, float quantization_multiplier,
+                                              size_t cols, size_t rows) {
+  sb::host_quantize(weights, prepared, quantization_multiplier, cols * rows);
+}
+
+int slimt_b200_qmm_affine(slimt_b200_ctx* ctx, const float* x, size_t M, size_t K, const int8_t* W, size_t N,
+                          const float* bias, float a_quant, float b_quant, const uint32_t* indices, size_t n_indices,
+                          float* y) {
+  return sb::qmm_affine_host(ctx->c, x, M, K, W, N, bias, a_quant, b_quant, indices, n_indices, y, nullptr, nullptr);
+}
+
+int slimt_b200_qmm_affine_debug(slimt_b200_ctx* ctx, const float* x, size_t M, size_t K, const int8_t* W, size_t N,
+                                const float* bias, float a_quant, float b_quant, const uint32_t* indices,
+                                size_t n_indices, float* y, int8_t* qa_out, int32_t* acc_out) {
+  return sb::qmm_affine_host(ctx->c, x, M, K, W, N, bias, a_quant, b_quant, indices, n_indices, y, qa_out, acc_out);
+}
+
+int slimt_b200_model_create(slimt_b200_ctx* ctx, const void* model_bin, size_t bytes,
+                            const slimt_b200_model_config* config, slimt_b200_model** out) {
+  if (config->feed_forward_depth != 2) {
+    sb::set_error("feed_forward_depth must be 2");
+    return 1;
+  }
+  auto* m = new (std::nothrow) slimt_b200_model();
+  if (!m) return 1;
+  if (m->m.load(&ctx->c, model_bin, bytes, config->encoder_layers, config->decoder_layers, config->num_heads)) {
+    m->m.destroy();
+    delete m;
+    return 1;
+  }
+  *out = m;
+  return 0;
+}
+
+void slimt_b200_model_destroy(slimt_b200_model* model) {
+  if (!model) return;
+  model->m.destroy();
+  delete model;
+}
+
+int slimt_b200_model_dims(const slimt_b200_model* model, int32_t* emb, int32_t* ffn, int32_t* vocab) {
+  *emb = model->m.E, *ffn = model->m.F, *vocab = model->m.V;
+  return 0;
+}
+
+int slimt_b200_model_forward(slimt_b200_model* model, slimt_b200_forward_io* io) {
+  sb::ForwardArgs a;
+  a.tokens = io->tokens, a.lengths = io->lengths, a.B = io->batch, a.T = io->seq;
+  a.limit_factor = io->limit_factor;
+  a.shortlist = io->shortlist, a.n_shortlist = io->n_shortlist;
+  a.forced = io->forced, a.device_io = io->device_io != 0;
+  a.step_tokens = io->step_tokens;
+  a.encoder_out = io->encoder_out, a.logits = io->logits, a.alignment = io->alignment;
+  int rc = sb::model_forward(model->m, a);
+  io->steps = a.steps;
+  io->target_tokens = a.target_tokens;
+  return rc;
+}
+
+int slimt_b200_translate(slimt_b200_model* model, slimt_b200_translate_io* io) {
+  sb::Model& m = model->m;
+  sb::Context& c = *m.ctx;
+  const uint64_t l0 = c.launches, h0 = c.h2d_bytes, d0 = c.d2h_bytes;
+  sb::ShortlistGenerator gen;
+  const bool use_sl = io->shortlist_bin != nullptr && io->shortlist_bytes > 0;
+  if (use_sl && gen.load(io->shortlist_bin, io->shortlist_bytes)) return 1;
+
+  sb::Batcher batcher(io->max_words);
+  for (size_t i = 0; i < io->n_sentences; i++) batcher.enqueue(i, io->offsets[i + 1] - io->offsets[i]);
+
+  std::vector<std::vector<uint32_t>> targets(io->n_sentences);
+  io->target_tokens = 0, io->batches = 0, io->device_ms = 0;
+  cudaSetDevice(c.device);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0), cudaEventCreate(&e1);
+  cudaEventRecord(e0, c.stream);
+  for (;;) {
+    size_t width = 0;
+    std::vector<size_t> batch = batcher.generate(&width);
+    if (batch.empty()) break;
+    // convert(): Batch -> padded Input (Frontend.cc:30-40; Input.cc:20-47), pad id 0
+    const size_t B = batch.size();
+    std::vector<uint32_t> tokens(B * width, 0u), lengths(B), words;
+    for (size_t r = 0; r < B; r++) {
+      const size_t s = batch[r];
+      const size_t len = io->offsets[s + 1] - io->offsets[s];
+      memcpy(tokens.data() + r * width, io->tokens + io->offsets[s], 4 * len);
+      lengths[r] = static_cast<uint32_t>(len);
+      words.insert(words.end(), io->tokens + io->offsets[s], io->tokens + io->offsets[s + 1]);
+    }
+    std::vector<uint32_t> sl;
+    if (use_sl) sl = gen.generate(words.data(), words.size(), m.V);
+    const size_t max_steps = static_cast<size_t>(io->limit_factor * static_cast<float>(width));
+    std::vector<uint32_t> steps(std::max<size_t>(1, max_steps) * B);
+    sb::ForwardArgs a;
+    a.tokens = tokens.data(), a.lengths = lengths.data(), a.B = B, a.T = width;
+    a.limit_factor = io->limit_factor;
+    a.shortlist = use_sl ? sl.data() : nullptr, a.n_shortlist = sl.size();
+    a.step_tokens = steps.data();
+    if (sb::model_forward(m, a)) {
+      cudaEventDestroy(e0), cudaEventDestroy(e1);
+      return 1;
+    }
+    // record() (Model.cc:127-137): keep tokens up to and including the first EOS
+    for (size_t r = 0; r < B; r++) {
+      std::vector<uint32_t>& t = targets[batch[r]];
+      for (size_t st = 0; st < a.steps; st++) {
+        const uint32_t w = steps[st * B + r];
+        t.push_back(w);
+        if (w == 0u) break;
+      }
+    }
+    io->target_tokens += a.target_tokens;
+    io->batches += 1;
+  }
+  cudaEventRecord(e1, c.stream);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0), cudaEventDestroy(e1);
+  io->device_ms = ms;
+
+  uint64_t off = 0;
+  for (size_t i = 0; i < io->n_sentences; i++) {
+    if (io->out_offsets) io->out_offsets[i] = off;
+    if (io->out_tokens) {
+      if (off + targets[i].size() > io->out_capacity) {
+        sb::set_error("out_tokens capacity too small");
+        return 1;
+      }
+      memcpy(io->out_tokens + off, targets[i].data(), 4 * targets[i].size());
+    }
+    off += targets[i].size();
+  }
+  if (io->out_offsets) io->out_offsets[io->n_sentences] = off;
+  io->kernel_launches = c.launches - l0;
+  io->h2d_bytes = c.h2d_bytes - h0;
+  io->d2h_bytes = c.d2h_bytes - d0;
+  return 0;
+}
+
+uint64_t slimt_b200_kernel_launches(const slimt_b200_ctx* ctx) { return ctx->c.launches; }
+
+}  // extern "C"

@@ -1,0 +1,863 @@
+// See engine.cuh.
+#include "engine.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace sb {
+
+namespace {
+thread_local std::string g_error;
+}
+void set_error(const std::string& msg) { g_error = msg; }
+const char* last_error() { return g_error.c_str(); }
+
+// ------------------------------------------------------------------ host exact helpers
+// clamp(rne(x*mult), -127, 127) with x86 cvtps2dq overflow semantics (see exact_math.cuh quantize1).
+void host_quantize(const float* x, int8_t* q, float mult, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    float t = x[i] * mult;
+    int v;
+    if (!(t == t) || t >= 2147483648.0f || t < -2147483648.0f) {
+      v = -127;
+    } else {
+      v = static_cast<int>(lrintf(t));
+      v = std::max(-127, std::min(127, v));
+    }
+    q[i] = static_cast<int8_t>(v);
+  }
+}
+
+// Int8Shift::PrepareBias with UnquantizeAndAddBiasAndWrite (qmm/Intgemm.inl.cc:112-128):
+// pb[n] = float(colsum[n]) * ((-1*((127/aq)*(127/bq)))/127) + bias[n]; c127[n] = 127*colsum[n].
+void host_prepare_bias(const int8_t* Bt, const float* bias, float aq, float bq, size_t K, size_t N, float* pb,
+                       int32_t* c127) {
+  const float a_alpha = 127.0f / aq;
+  const float b_alpha = 127.0f / bq;
+  const float m = (-1.0f * (a_alpha * b_alpha)) / 127.0f;
+  for (size_t n = 0; n < N; n++) {
+    int32_t cs = 0;
+    const int8_t* row = Bt + n * K;
+    for (size_t k = 0; k < K; k++) cs += row[k];
+    volatile float prod = static_cast<float>(cs) * m;  // keep mul and add separate (no contraction)
+    pb[n] = prod + (bias ? bias[n] : 0.0f);
+    c127[n] = 127 * cs;
+  }
+}
+
+// ------------------------------------------------------------------ context
+int Context::init(int dev) {
+  device = dev;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+              "); slimt_b200 has no CPU fallback");
+    return 1;
+  }
+  SB_CUDA(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  SB_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("slimt_b200 requires an sm_100a (B200) device, found sm_" + std::to_string(prop.major) +
+              std::to_string(prop.minor));
+    return 1;
+  }
+  SB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  SB_CUDA(cudaEventCreate(&ev0));
+  SB_CUDA(cudaEventCreate(&ev1));
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  SB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return 1;
+  }
+  encode_tiled = reinterpret_cast<decltype(encode_tiled)>(fn);
+  return 0;
+}
+
+void Context::destroy() {
+  cudaSetDevice(device);
+  if (arena) cudaFree(arena);
+  if (flush_buf) cudaFree(flush_buf);
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+int Context::reserve(size_t bytes) {
+  arena_used = 0;
+  if (bytes <= arena_bytes) return 0;
+  SB_CUDA(cudaStreamSynchronize(stream));
+  if (arena) SB_CUDA(cudaFree(arena));
+  arena = nullptr;
+  arena_bytes = 0;
+  size_t want = bytes + (bytes >> 3);
+  SB_CUDA(cudaMalloc(&arena, want));
+  arena_bytes = want;
+  return 0;
+}
+
+int Context::make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)) + " (rows=" +
+              std::to_string(rows) + ", cols=" + std::to_string(cols) + ")");
+    return 1;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ model loading
+namespace {
+
+struct Item {
+  std::string name;
+  uint64_t type = 0;
+  std::vector<int> shape;
+  const char* data = nullptr;
+  uint64_t bytes = 0;
+  size_t elements() const {
+    size_t n = 1;
+    for (int d : shape) n *= static_cast<size_t>(d);
+    return n;
+  }
+};
+
+constexpr uint64_t kTypeF32 = 0x0404, kTypeIG8 = 0x4101;
+
+// marian binary v1 (slimt/Io.cc:114-153, Io.hh:19-29)
+int parse_items(const void* bin, size_t bytes, std::map<std::string, Item>& out) {
+  const char* p = static_cast<const char*>(bin);
+  const char* end = p + bytes;
+  auto rd64 = [&p]() {
+    uint64_t v;
+    memcpy(&v, p, 8);
+    p += 8;
+    return v;
+  };
+  if (bytes < 16) {
+    set_error("model image too small");
+    return 1;
+  }
+  uint64_t version = rd64();
+  if (version != 1) {
+    set_error("Binary file versions do not match: " + std::to_string(version) + " (file) != 1 (expected)");
+    return 1;
+  }
+  uint64_t n = rd64();
+  struct Hdr {
+    uint64_t name_len, type, shape_len, data_len;
+  };
+  std::vector<Hdr> hdrs(n);
+  for (auto& h : hdrs) {
+    h.name_len = rd64(), h.type = rd64(), h.shape_len = rd64(), h.data_len = rd64();
+  }
+  std::vector<Item> items(n);
+  for (uint64_t i = 0; i < n; i++) {
+    items[i].name = std::string(p, hdrs[i].name_len - 1);
+    items[i].type = hdrs[i].type;
+    p += hdrs[i].name_len;
+  }
+  for (uint64_t i = 0; i < n; i++) {
+    items[i].shape.resize(hdrs[i].shape_len);
+    memcpy(items[i].shape.data(), p, 4 * hdrs[i].shape_len);
+    p += 4 * hdrs[i].shape_len;
+  }
+  uint64_t pad = rd64();
+  p += pad;
+  for (uint64_t i = 0; i < n; i++) {
+    items[i].data = p;
+    items[i].bytes = hdrs[i].data_len;
+    p += hdrs[i].data_len;
+    if (p > end) {
+      set_error("model image truncated at item " + items[i].name);
+      return 1;
+    }
+    if (items[i].type != kTypeF32 && items[i].type != kTypeIG8 && items[i].type != 0x0101) {
+      set_error("Incompatible type in model item " + items[i].name);
+      return 1;
+    }
+    out[items[i].name] = items[i];
+  }
+  return 0;
+}
+
+}  // namespace
+
+int Model::load(Context* c, const void* bin, size_t bytes, int enc_layers, int dec_layers, int heads) {
+  ctx = c;
+  H = heads;
+  SB_CUDA(cudaSetDevice(c->device));
+  std::map<std::string, Item> items;
+  if (parse_items(bin, bytes, items)) return 1;
+
+  auto need = [&items](const std::string& name) -> const Item* {
+    auto it = items.find(name);
+    if (it == items.end()) {
+      set_error("model is missing parameter " + name);
+      return nullptr;
+    }
+    return &it->second;
+  };
+  auto upload = [this](const void* src, size_t nbytes, void** dst) -> int {
+    SB_CUDA(cudaMalloc(dst, nbytes));
+    owned.push_back(*dst);
+    SB_CUDA(cudaMemcpy(*dst, src, nbytes, cudaMemcpyHostToDevice));
+    ctx->h2d_bytes += nbytes;
+    return 0;
+  };
+  auto f32_vec = [&](const std::string& name, size_t n, float** dst) -> int {
+    const Item* it = need(name);
+    if (!it) return 1;
+    if (it->elements() != n) {
+      set_error("parameter " + name + " has unexpected size");
+      return 1;
+    }
+    return upload(it->data, n * 4, reinterpret_cast<void**>(dst));
+  };
+  auto scalar = [&](const std::string& name, float* v) -> int {
+    const Item* it = need(name);
+    if (!it) return 1;
+    memcpy(v, it->data, 4);
+    return 0;
+  };
+  // ig8 item [K,N]: blob = N rows of K int8 (B^T) then the f32 b_quant (Io.cc:227-242).
+  auto weight = [&](const std::string& wname, const std::string& bname, DevWeight& w, const int8_t* override_q = nullptr,
+                    const std::string& aq_name = "") -> int {
+    const Item* it = need(wname);
+    if (!it) return 1;
+    int K = it->shape[0], N = it->shape[1];
+    const int8_t* q = reinterpret_cast<const int8_t*>(it->data);
+    if (wname == "Wemb") std::swap(K, N);  // stored [V][E]: as an output weight K = E, N = V
+    memcpy(&w.bq, it->data + static_cast<size_t>(K) * N, 4);
+    if (override_q) q = override_q;
+    if (scalar(aq_name.empty() ? wname + "_QuantMultA" : aq_name, &w.aq)) return 1;
+    w.K = K, w.N = N;
+    w.um = 1.0f / (w.aq * w.bq);
+    const float* bias = nullptr;
+    if (!bname.empty()) {
+      const Item* b = need(bname);
+      if (!b) return 1;
+      if (b->elements() != static_cast<size_t>(N)) {
+        set_error("bias " + bname + " has unexpected size");
+        return 1;
+      }
+      bias = reinterpret_cast<const float*>(b->data);
+    }
+    if (K % 64 != 0 || N % 8 != 0) {
+      set_error("weight " + wname + ": intgemm shape preconditions violated (K % 64, N % 8)");
+      return 1;
+    }
+    std::vector<float> pb(N);
+    std::vector<int32_t> c127(N);
+    host_prepare_bias(q, bias, w.aq, w.bq, K, N, pb.data(), c127.data());
+    if (upload(q, static_cast<size_t>(K) * N, reinterpret_cast<void**>(&w.w))) return 1;
+    if (upload(pb.data(), 4ul * N, reinterpret_cast<void**>(&w.pb))) return 1;
+    if (upload(c127.data(), 4ul * N, reinterpret_cast<void**>(&w.c127))) return 1;
+    return 0;
+  };
+  auto ln = [&](const std::string& prefix, DevLN& l) -> int {
+    return f32_vec(prefix + "_ln_scale", E, &l.scale) || f32_vec(prefix + "_ln_bias", E, &l.bias);
+  };
+  auto attention = [&](const std::string& prefix, AttnW& a) -> int {
+    return weight(prefix + "_Wq", prefix + "_bq", a.q) || weight(prefix + "_Wk", prefix + "_bk", a.k) ||
+           weight(prefix + "_Wv", prefix + "_bv", a.v) || weight(prefix + "_Wo", prefix + "_bo", a.o) ||
+           ln(prefix + "_Wo", a.ln);
+  };
+  auto ffn = [&](const std::string& prefix, FfnW& f) -> int {
+    return weight(prefix + "_ffn_W1", prefix + "_ffn_b1", f.w1) || weight(prefix + "_ffn_W2", prefix + "_ffn_b2", f.w2) ||
+           ln(prefix + "_ffn_ffn", f.ln);
+  };
+
+  const Item* wemb = need("Wemb");
+  if (!wemb) return 1;
+  V = wemb->shape[0];
+  E = wemb->shape[1];
+  if (E % H != 0 || (E / H != 32 && E / H != 64)) {
+    set_error("unsupported head size " + std::to_string(E / std::max(1, H)));
+    return 1;
+  }
+  if (E != 256 && E != 512) {
+    set_error("unsupported embedding size " + std::to_string(E) + " (256 and 512 are built)");
+    return 1;
+  }
+  dh = E / H;
+  memcpy(&emb_qm, wemb->data + static_cast<size_t>(V) * E, 4);
+  inv_qm = 1 / emb_qm;  // Io.cc:281: `(1 / quantization_multiplier)` in float
+  sqrt_e = sqrtf(static_cast<float>(E));
+  if (upload(wemb->data, static_cast<size_t>(V) * E, reinterpret_cast<void**>(&emb_q))) return 1;
+
+  // Output layer: dequantise the embedding and quantise it again (Io.cc:183-224): identical to the
+  // stored bytes except that -128 becomes -127.
+  {
+    std::vector<float> deq(static_cast<size_t>(V) * E);
+    const int8_t* q = reinterpret_cast<const int8_t*>(wemb->data);
+    for (size_t i = 0; i < deq.size(); i++) deq[i] = static_cast<float>(q[i]) * inv_qm;
+    std::vector<int8_t> req(deq.size());
+    host_quantize(deq.data(), req.data(), emb_qm, deq.size());
+    if (weight("Wemb", "decoder_ff_logit_out_b", out, req.data(), "none_QuantMultA")) return 1;
+  }
+
+  enc.resize(enc_layers);
+  for (int i = 0; i < enc_layers; i++) {
+    const std::string p = "encoder_l" + std::to_string(i + 1);
+    if (attention(p + "_self", enc[i].self) || ffn(p, enc[i].ffn)) return 1;
+  }
+  dec.resize(dec_layers);
+  for (int j = 0; j < dec_layers; j++) {
+    const std::string p = "decoder_l" + std::to_string(j + 1);
+    if (weight(p + "_rnn_W", "", dec[j].rnn_w) || weight(p + "_rnn_Wf", p + "_rnn_bf", dec[j].rnn_wf) ||
+        ln(p + "_rnn_ffn", dec[j].rnn_ln) || attention(p + "_context", dec[j].ctx) || ffn(p, dec[j].ffn))
+      return 1;
+  }
+  F = enc_layers ? enc[0].ffn.w1.N : (dec_layers ? dec[0].ffn.w1.N : 0);
+
+  // sinusoidal_signal (TensorOps.cc:245-265), evaluated with the host libm like the reference
+  max_pos = 1024;
+  std::vector<float> table(static_cast<size_t>(max_pos) * E);
+  {
+    float num_timescales = static_cast<float>(E) / 2;
+    float inc = std::log(10000.0F) / (num_timescales - 1.0F);
+    for (size_t pp = 0; pp < static_cast<size_t>(max_pos); ++pp) {
+      for (int i = 0; i < num_timescales; ++i) {
+        float v = pp * std::exp(i * -inc);
+        table[pp * E + i] = std::sin(v);
+        table[pp * E + i + static_cast<int>(num_timescales)] = std::cos(v);
+      }
+    }
+  }
+  if (upload(table.data(), table.size() * 4, reinterpret_cast<void**>(&pos))) return 1;
+  return 0;
+}
+
+void Model::destroy() {
+  if (ctx) cudaSetDevice(ctx->device);
+  for (void* p : owned) cudaFree(p);
+  owned.clear();
+}
+
+// ------------------------------------------------------------------ GEMM helpers
+namespace {
+
+int pick_bn(int M, int N, int n_prob, bool full_row) {
+  if (full_row) return N;  // RES_LN: one CTA owns whole rows
+  const int m_tiles = (M + kBM - 1) / kBM;
+  int bn = 256;
+  while (bn > 64 && static_cast<long>(m_tiles) * ((N + bn - 1) / bn) * n_prob < 148) bn >>= 1;
+  if (N < bn) bn = std::max(64, 1 << static_cast<int>(ceil(log2(static_cast<double>(N)))));
+  return std::min(bn, 256);
+}
+
+struct GemmCall {
+  Context* c;
+  GemmBatch b{};
+  int n = 0;
+  int epi = EPI_F32;
+  int bn = 256;
+  GemmCall(Context* ctx, int M, int N, int K, int epilogue, int n_prob_hint = 1) : c(ctx), epi(epilogue) {
+    b.M = M, b.N = N, b.K = K;
+    bn = pick_bn(M, N, n_prob_hint, epilogue == EPI_RES_LN);
+  }
+  // adds one problem; returns its slot (or nullptr on failure)
+  GemmProblem* add(const int8_t* A, const int8_t* Wt, const int32_t* c127, const float* pb, float um) {
+    GemmProblem& p = b.prob[n];
+    memset(&p, 0, sizeof(p));
+    const uint32_t box_b = static_cast<uint32_t>(std::min(bn, 256));
+    if (c->make_map(&p.tma_a, A, b.M, b.K, kBM)) return nullptr;
+    if (c->make_map(&p.tma_b, Wt, b.N, b.K, box_b)) return nullptr;
+    p.c127 = c127, p.pb = pb, p.um = um;
+    p.ln_eps = 1e-6f;  // TensorOps.hh:67-68
+    n++;
+    return &p;
+  }
+  GemmProblem* add(const int8_t* A, const DevWeight& w) { return add(A, w.w, w.c127, w.pb, w.um); }
+  int launch() {
+    launch_gemm_i8(b, n, epi, bn, c->stream);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error(std::string("GEMM launch failed: ") + cudaGetErrorString(e));
+      return 1;
+    }
+    return 0;
+  }
+};
+
+QuantOuts qouts() {
+  QuantOuts q;
+  memset(&q, 0, sizeof(q));
+  return q;
+}
+void qadd(QuantOuts& q, int8_t* p, float aq) {
+  q.ptr[q.n] = p;
+  q.aq[q.n] = aq;
+  q.n++;
+}
+void padd(GemmProblem* p, int8_t* ptr, float aq) {
+  p->qout[p->n_qout] = ptr;
+  p->aq_out[p->n_qout] = aq;
+  p->n_qout++;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ operator API
+int qmm_affine_host(Context& c, const float* x, size_t M, size_t K, const int8_t* W, size_t N, const float* bias,
+                    float aq, float bq, const uint32_t* indices, size_t n_idx, float* y, int8_t* qa_out,
+                    int32_t* acc_out) {
+  SB_CUDA(cudaSetDevice(c.device));
+  if (K % 64 != 0 || N % 8 != 0 || (indices && n_idx % 8 != 0)) {
+    set_error("qmm::affine shape preconditions violated: K % 64 == 0, N % 8 == 0, indices % 8 == 0");
+    return 1;
+  }
+  if (M == 0) return 0;
+  // PrepareBias on the FULL B, then gather (qmm/Intgemm.inl.cc:33-66)
+  std::vector<float> pb(N);
+  std::vector<int32_t> c127(N);
+  host_prepare_bias(W, bias, aq, bq, K, N, pb.data(), c127.data());
+  const size_t Nout = indices ? n_idx : N;
+  const size_t need = M * K * 5 + N * K + N * 8 + Nout * K + Nout * 8 + n_idx * 4 + M * Nout * 8 + 16 * 256;
+  if (c.reserve(need)) return 1;
+  float* dx = c.take<float>(M * K);
+  int8_t* dqa = c.take<int8_t>(M * K);
+  int8_t* dW = c.take<int8_t>(N * K);
+  float* dpb = c.take<float>(N);
+  int32_t* dc = c.take<int32_t>(N);
+  float* dy = c.take<float>(M * Nout);
+  int32_t* dacc = c.take<int32_t>(M * Nout);
+  cudaStream_t s = c.stream;
+  SB_CUDA(cudaMemcpyAsync(dx, x, M * K * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(dW, W, N * K, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(dpb, pb.data(), N * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(dc, c127.data(), N * 4, cudaMemcpyHostToDevice, s));
+  c.h2d_bytes += M * K * 4 + N * K + N * 8;
+  const int8_t* Wuse = dW;
+  const float* pbuse = dpb;
+  const int32_t* cuse = dc;
+  if (indices) {
+    uint32_t* didx = c.take<uint32_t>(n_idx);
+    int8_t* dWs = c.take<int8_t>(n_idx * K);
+    float* dpbs = c.take<float>(n_idx);
+    int32_t* dcs = c.take<int32_t>(n_idx);
+    SB_CUDA(cudaMemcpyAsync(didx, indices, n_idx * 4, cudaMemcpyHostToDevice, s));
+    launch_gather_rows(dW, dpb, dc, didx, static_cast<int>(n_idx), static_cast<int>(K), dWs, dpbs, dcs, s);
+    c.launches++;
+    Wuse = dWs, pbuse = dpbs, cuse = dcs;
+  }
+  QuantOuts q = qouts();
+  qadd(q, dqa, aq);
+  launch_quantize(dx, M * K, q, s);
+  c.launches++;
+  const float um = 1.0f / (aq * bq);
+  {
+    GemmCall g(&c, static_cast<int>(M), static_cast<int>(Nout), static_cast<int>(K), EPI_F32);
+    GemmProblem* p = g.add(dqa, Wuse, cuse, pbuse, um);
+    if (!p) return 1;
+    p->out = dy, p->ldo = static_cast<int>(Nout);
+    if (g.launch()) return 1;
+  }
+  if (acc_out) {
+    GemmCall g(&c, static_cast<int>(M), static_cast<int>(Nout), static_cast<int>(K), EPI_ACC);
+    GemmProblem* p = g.add(dqa, Wuse, cuse, pbuse, um);
+    if (!p) return 1;
+    p->out = dacc, p->ldo = static_cast<int>(Nout);
+    if (g.launch()) return 1;
+    SB_CUDA(cudaMemcpyAsync(acc_out, dacc, M * Nout * 4, cudaMemcpyDeviceToHost, s));
+  }
+  if (qa_out) SB_CUDA(cudaMemcpyAsync(qa_out, dqa, M * K, cudaMemcpyDeviceToHost, s));
+  SB_CUDA(cudaMemcpyAsync(y, dy, M * Nout * 4, cudaMemcpyDeviceToHost, s));
+  c.d2h_bytes += M * Nout * 4;
+  SB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// ------------------------------------------------------------------ Model::forward
+int model_forward(Model& m, ForwardArgs& a) {
+  Context& c = *m.ctx;
+  SB_CUDA(cudaSetDevice(c.device));
+  cudaStream_t s = c.stream;
+  const int B = static_cast<int>(a.B), T = static_cast<int>(a.T), E = m.E, F = m.F, H = m.H, dh = m.dh;
+  const int R = B * T;
+  const int Le = static_cast<int>(m.enc.size()), Ld = static_cast<int>(m.dec.size());
+  a.steps = 0;
+  a.target_tokens = 0;
+  if (B == 0 || T == 0) return 0;
+  if (T > m.max_pos || T > 256) {
+    set_error("sequence length " + std::to_string(T) + " exceeds the supported maximum of 256");
+    return 1;
+  }
+  if (Ld < 1 || 2 * Ld > kMaxQuantOut) {
+    set_error("decoder_layers must be 1 or 2");
+    return 1;
+  }
+  // Model.cc:160: size_t max_seq_length = limit_factor * source_sequence_length (float product, truncated)
+  const int max_steps = static_cast<int>(static_cast<size_t>(a.limit_factor * static_cast<float>(T)));
+  const bool use_sl = a.shortlist != nullptr && a.n_shortlist > 0;
+  const int Nout = use_sl ? static_cast<int>(a.n_shortlist) : m.V;
+  if (use_sl && a.n_shortlist % 8 != 0) {
+    set_error("shortlist size must be a multiple of 8");
+    return 1;
+  }
+
+  // ---- workspace
+  size_t need = 0;
+  auto acc = [&need](size_t bytes) { need += (bytes + 255) & ~size_t(255); };
+  acc(4ul * R), acc(4ul * B);                                   // tokens, lengths
+  acc(4ul * R * E), acc(4ul * R * E);                           // x0, x1
+  for (int i = 0; i < 4; i++) acc(1ul * R * E);                 // qa[4]
+  for (int i = 0; i < 3; i++) acc(4ul * R * E);                 // Q K V
+  acc(1ul * R * E), acc(1ul * R * F);                           // attn_q, ffn_q
+  for (int i = 0; i < 2 * Ld; i++) acc(4ul * R * E);            // cross K/V caches
+  for (int i = 0; i < 9 + Ld; i++) acc(4ul * B * E);            // decode f32 rows
+  for (int i = 0; i < 8; i++) acc(1ul * B * E);                 // decode int8 rows
+  acc(1ul * B * F);
+  acc(8ul * B), acc(B), acc(4ul * B), acc(256);                 // best, done, tgt_len, counters
+  acc(4ul * std::max(1, max_steps) * B);                        // step tokens
+  if (a.forced) acc(4ul * std::max(1, max_steps) * B);
+  if (use_sl) acc(4ul * Nout), acc(1ul * Nout * E), acc(4ul * Nout), acc(4ul * Nout);
+  if (a.logits) acc(4ul * B * Nout);
+  if (a.alignment) acc(4ul * B * T);
+  need += 64 * 256;
+  if (c.reserve(need)) return 1;
+
+  uint32_t* d_tokens = nullptr;
+  uint32_t* d_lengths = nullptr;
+  if (a.device_io) {
+    d_tokens = const_cast<uint32_t*>(a.tokens);
+    d_lengths = const_cast<uint32_t*>(a.lengths);
+    c.take<uint32_t>(R), c.take<uint32_t>(B);
+  } else {
+    d_tokens = c.take<uint32_t>(R);
+    d_lengths = c.take<uint32_t>(B);
+    SB_CUDA(cudaMemcpyAsync(d_tokens, a.tokens, 4ul * R, cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(d_lengths, a.lengths, 4ul * B, cudaMemcpyHostToDevice, s));
+    c.h2d_bytes += 4ul * R + 4ul * B;
+  }
+  float* x0 = c.take<float>(static_cast<size_t>(R) * E);
+  float* x1 = c.take<float>(static_cast<size_t>(R) * E);
+  int8_t* qa[4];
+  for (auto& p : qa) p = c.take<int8_t>(static_cast<size_t>(R) * E);
+  float* Qb = c.take<float>(static_cast<size_t>(R) * E);
+  float* Kb = c.take<float>(static_cast<size_t>(R) * E);
+  float* Vb = c.take<float>(static_cast<size_t>(R) * E);
+  int8_t* attn_q = c.take<int8_t>(static_cast<size_t>(R) * E);
+  int8_t* ffn_q = c.take<int8_t>(static_cast<size_t>(R) * F);
+  std::vector<float*> Kc(Ld), Vc(Ld);
+  for (int l = 0; l < Ld; l++) {
+    Kc[l] = c.take<float>(static_cast<size_t>(R) * E);
+    Vc[l] = c.take<float>(static_cast<size_t>(R) * E);
+  }
+
+  // ---- embedding (Model.cc:195-197)
+  {
+    QuantOuts q = qouts();
+    if (Le > 0) {
+      qadd(q, qa[0], m.enc[0].self.q.aq), qadd(q, qa[1], m.enc[0].self.k.aq), qadd(q, qa[2], m.enc[0].self.v.aq);
+    }
+    launch_embed(d_tokens, m.emb_q, m.inv_qm, m.sqrt_e, m.pos, R, T, E, 1, 0, x0, q, s);
+    c.launches++;
+  }
+
+  // ---- encoder (Transformer.cc:57-69; EncoderLayer::forward Modules.cc:321-334)
+  for (int i = 0; i < Le; i++) {
+    const EncLayerW& L = m.enc[i];
+    {
+      GemmCall g(&c, R, E, E, EPI_F32, 3);
+      GemmProblem* pq = g.add(qa[0], L.self.q);
+      GemmProblem* pk = g.add(qa[1], L.self.k);
+      GemmProblem* pv = g.add(qa[2], L.self.v);
+      if (!pq || !pk || !pv) return 1;
+      pq->out = Qb, pk->out = Kb, pv->out = Vb;
+      pq->ldo = pk->ldo = pv->ldo = E;
+      if (g.launch()) return 1;
+    }
+    {
+      QuantOuts q = qouts();
+      qadd(q, attn_q, L.self.o.aq);
+      launch_self_attention(Qb, Kb, Vb, d_lengths, B, T, H, dh, nullptr, q, s);
+      c.launches++;
+    }
+    {
+      GemmCall g(&c, R, E, E, EPI_RES_LN);
+      GemmProblem* p = g.add(attn_q, L.self.o);
+      if (!p) return 1;
+      p->residual = x0, p->ln_scale = L.self.ln.scale, p->ln_bias = L.self.ln.bias;
+      p->out = x1;
+      padd(p, qa[0], L.ffn.w1.aq);
+      if (g.launch()) return 1;
+    }
+    {
+      GemmCall g(&c, R, F, E, EPI_QUANT);
+      GemmProblem* p = g.add(qa[0], L.ffn.w1);
+      if (!p) return 1;
+      p->relu = 1;
+      padd(p, ffn_q, L.ffn.w2.aq);
+      if (g.launch()) return 1;
+    }
+    {
+      GemmCall g(&c, R, E, F, EPI_RES_LN);
+      GemmProblem* p = g.add(ffn_q, L.ffn.w2);
+      if (!p) return 1;
+      p->residual = x1, p->ln_scale = L.ffn.ln.scale, p->ln_bias = L.ffn.ln.bias;
+      p->out = x0;
+      if (i + 1 < Le) {
+        const EncLayerW& Nx = m.enc[i + 1];
+        padd(p, qa[0], Nx.self.q.aq), padd(p, qa[1], Nx.self.k.aq), padd(p, qa[2], Nx.self.v.aq);
+      } else {
+        for (int l = 0; l < Ld; l++) padd(p, qa[2 * l], m.dec[l].ctx.k.aq), padd(p, qa[2 * l + 1], m.dec[l].ctx.v.aq);
+      }
+      if (g.launch()) return 1;
+    }
+  }
+  if (Le == 0) {  // degenerate: quantize the embedding for the decoder's K/V projections
+    QuantOuts q = qouts();
+    for (int l = 0; l < Ld; l++) qadd(q, qa[2 * l], m.dec[l].ctx.k.aq), qadd(q, qa[2 * l + 1], m.dec[l].ctx.v.aq);
+    launch_quantize(x0, static_cast<size_t>(R) * E, q, s);
+    c.launches++;
+  }
+  if (a.encoder_out) {
+    SB_CUDA(cudaMemcpyAsync(a.encoder_out, x0, 4ul * R * E, cudaMemcpyDeviceToHost, s));
+    c.d2h_bytes += 4ul * R * E;
+  }
+
+  // ---- cross-attention K/V, once per batch (the reference re-projects them every step: Modules.cc:244-249)
+  for (int l = 0; l < Ld; l++) {
+    GemmCall g(&c, R, E, E, EPI_F32, 2);
+    GemmProblem* pk = g.add(qa[2 * l], m.dec[l].ctx.k);
+    GemmProblem* pv = g.add(qa[2 * l + 1], m.dec[l].ctx.v);
+    if (!pk || !pv) return 1;
+    pk->out = Kc[l], pv->out = Vc[l];
+    pk->ldo = pv->ldo = E;
+    if (g.launch()) return 1;
+  }
+
+  // ---- decoder state (Model.cc:111-185)
+  float* xd = c.take<float>(static_cast<size_t>(B) * E);
+  float* fb = c.take<float>(static_cast<size_t>(B) * E);
+  float* wxb = c.take<float>(static_cast<size_t>(B) * E);
+  float* hb = c.take<float>(static_cast<size_t>(B) * E);
+  float* qd = c.take<float>(static_cast<size_t>(B) * E);
+  float* yb = c.take<float>(static_cast<size_t>(B) * E);
+  float* zb[2] = {c.take<float>(static_cast<size_t>(B) * E), c.take<float>(static_cast<size_t>(B) * E)};
+  c.take<float>(static_cast<size_t>(B) * E);
+  std::vector<float*> state(Ld);
+  for (int l = 0; l < Ld; l++) state[l] = c.take<float>(static_cast<size_t>(B) * E);
+  int8_t* xq[2] = {c.take<int8_t>(static_cast<size_t>(B) * E), c.take<int8_t>(static_cast<size_t>(B) * E)};
+  int8_t* zq[2] = {c.take<int8_t>(static_cast<size_t>(B) * E), c.take<int8_t>(static_cast<size_t>(B) * E)};
+  int8_t* hq = c.take<int8_t>(static_cast<size_t>(B) * E);
+  int8_t* caq = c.take<int8_t>(static_cast<size_t>(B) * E);
+  int8_t* yq = c.take<int8_t>(static_cast<size_t>(B) * E);
+  int8_t* oq = c.take<int8_t>(static_cast<size_t>(B) * E);
+  int8_t* fq = c.take<int8_t>(static_cast<size_t>(B) * F);
+  unsigned long long* best = c.take<unsigned long long>(B);
+  uint8_t* done = c.take<uint8_t>(B);
+  uint32_t* tgt_len = c.take<uint32_t>(B);
+  int* counters = c.take<int>(64);  // [0] n_done, [1] step counter, [2] ticket
+  uint32_t* d_steps = nullptr;
+  if (a.device_io) {
+    d_steps = a.step_tokens;
+    c.take<uint32_t>(static_cast<size_t>(std::max(1, max_steps)) * B);
+  } else {
+    d_steps = c.take<uint32_t>(static_cast<size_t>(std::max(1, max_steps)) * B);
+  }
+  const uint32_t* d_forced = nullptr;
+  if (a.forced) {
+    if (a.device_io) {
+      d_forced = a.forced;
+    } else {
+      uint32_t* t = c.take<uint32_t>(static_cast<size_t>(std::max(1, max_steps)) * B);
+      SB_CUDA(cudaMemcpyAsync(t, a.forced, 4ul * max_steps * B, cudaMemcpyHostToDevice, s));
+      c.h2d_bytes += 4ul * max_steps * B;
+      d_forced = t;
+    }
+  }
+  const uint32_t* d_sl = nullptr;
+  const int8_t* Wout = m.out.w;
+  const float* pb_out = m.out.pb;
+  const int32_t* c127_out = m.out.c127;
+  if (use_sl) {
+    if (a.device_io) {
+      d_sl = a.shortlist;
+      c.take<uint32_t>(Nout);
+    } else {
+      uint32_t* t = c.take<uint32_t>(Nout);
+      SB_CUDA(cudaMemcpyAsync(t, a.shortlist, 4ul * Nout, cudaMemcpyHostToDevice, s));
+      c.h2d_bytes += 4ul * Nout;
+      d_sl = t;
+    }
+    // SelectColumnsB + bias gather, once per batch (qmm/Intgemm.inl.cc:49-66)
+    int8_t* Ws = c.take<int8_t>(static_cast<size_t>(Nout) * E);
+    float* pbs = c.take<float>(Nout);
+    int32_t* cs = c.take<int32_t>(Nout);
+    launch_gather_rows(m.out.w, m.out.pb, m.out.c127, d_sl, Nout, E, Ws, pbs, cs, s);
+    c.launches++;
+    Wout = Ws, pb_out = pbs, c127_out = cs;
+  }
+  float* d_logits = a.logits ? c.take<float>(static_cast<size_t>(B) * Nout) : nullptr;
+  float* d_align = a.alignment ? c.take<float>(static_cast<size_t>(B) * T) : nullptr;
+
+  for (int l = 0; l < Ld; l++) SB_CUDA(cudaMemsetAsync(state[l], 0, 4ul * B * E, s));  // Decoder::start_states
+  SB_CUDA(cudaMemsetAsync(best, 0, 8ul * B, s));
+  SB_CUDA(cudaMemsetAsync(done, 0, B, s));
+  SB_CUDA(cudaMemsetAsync(tgt_len, 0, 4ul * B, s));
+  SB_CUDA(cudaMemsetAsync(counters, 0, 256, s));
+
+  // step 0 input: zero embedding + position-0 signal (Transformer.cc:133-160)
+  {
+    QuantOuts q = qouts();
+    qadd(q, xq[0], m.dec[0].rnn_wf.aq), qadd(q, xq[1], m.dec[0].rnn_w.aq);
+    launch_embed(nullptr, m.emb_q, m.inv_qm, m.sqrt_e, m.pos, B, 1, E, 0, 1, xd, q, s);
+    c.launches++;
+  }
+
+  int executed = 0;
+  int host_done = 0;
+  for (int step = 0; step < max_steps; step++) {
+    const float* in_f = xd;
+    int8_t* const* in_q = xq;
+    for (int l = 0; l < Ld; l++) {
+      const DecLayerW& L = m.dec[l];
+      const bool last = (l + 1 == Ld);
+      {  // SSRU projections (Modules.cc:218-219)
+        GemmCall g(&c, B, E, E, EPI_F32, 2);
+        GemmProblem* pf = g.add(in_q[0], L.rnn_wf);
+        GemmProblem* pw = g.add(in_q[1], L.rnn_w);
+        if (!pf || !pw) return 1;
+        pf->out = fb, pw->out = wxb;
+        pf->ldo = pw->ldo = E;
+        if (g.launch()) return 1;
+      }
+      {
+        QuantOuts q = qouts();
+        qadd(q, hq, L.ctx.q.aq);
+        launch_ssru_ln(fb, wxb, state[l], in_f, L.rnn_ln.scale, L.rnn_ln.bias, 1e-6f, B, E, hb, q, s);
+        c.launches++;
+      }
+      {
+        GemmCall g(&c, B, E, E, EPI_F32);
+        GemmProblem* p = g.add(hq, L.ctx.q);
+        if (!p) return 1;
+        p->out = qd, p->ldo = E;
+        if (g.launch()) return 1;
+      }
+      {
+        QuantOuts q = qouts();
+        qadd(q, caq, L.ctx.o.aq);
+        launch_cross_attention(qd, Kc[l], Vc[l], d_lengths, B, T, H, dh, nullptr, q, last ? d_align : nullptr, s);
+        c.launches++;
+      }
+      {
+        GemmCall g(&c, B, E, E, EPI_RES_LN);
+        GemmProblem* p = g.add(caq, L.ctx.o);
+        if (!p) return 1;
+        p->residual = hb, p->ln_scale = L.ctx.ln.scale, p->ln_bias = L.ctx.ln.bias;
+        p->out = yb;
+        padd(p, yq, L.ffn.w1.aq);
+        if (g.launch()) return 1;
+      }
+      {
+        GemmCall g(&c, B, F, E, EPI_QUANT);
+        GemmProblem* p = g.add(yq, L.ffn.w1);
+        if (!p) return 1;
+        p->relu = 1;
+        padd(p, fq, L.ffn.w2.aq);
+        if (g.launch()) return 1;
+      }
+      {
+        GemmCall g(&c, B, E, F, EPI_RES_LN);
+        GemmProblem* p = g.add(fq, L.ffn.w2);
+        if (!p) return 1;
+        p->residual = yb, p->ln_scale = L.ffn.ln.scale, p->ln_bias = L.ffn.ln.bias;
+        if (last) {
+          p->out = nullptr;
+          padd(p, oq, m.out.aq);
+        } else {
+          p->out = zb[l & 1];
+          padd(p, zq[0], m.dec[l + 1].rnn_wf.aq), padd(p, zq[1], m.dec[l + 1].rnn_w.aq);
+        }
+        if (g.launch()) return 1;
+      }
+      in_f = zb[l & 1];
+      in_q = zq;
+    }
+    // output projection (+ shortlist) and greedy choice (Transformer.cc:176-182, 279-339)
+    if (d_logits) {
+      GemmCall g(&c, B, Nout, E, EPI_F32);
+      GemmProblem* p = g.add(oq, Wout, c127_out, pb_out, m.out.um);
+      if (!p) return 1;
+      p->out = d_logits, p->ldo = Nout;
+      if (g.launch()) return 1;
+      launch_argmax_rows(d_logits, B, Nout, best, s);
+      c.launches++;
+      SB_CUDA(cudaMemcpyAsync(a.logits + static_cast<size_t>(step) * B * Nout, d_logits, 4ul * B * Nout,
+                              cudaMemcpyDeviceToHost, s));
+      c.d2h_bytes += 4ul * B * Nout;
+    } else {
+      GemmCall g(&c, B, Nout, E, EPI_ARGMAX);
+      GemmProblem* p = g.add(oq, Wout, c127_out, pb_out, m.out.um);
+      if (!p) return 1;
+      p->best = best;
+      if (g.launch()) return 1;
+    }
+    if (d_align) {
+      SB_CUDA(cudaMemcpyAsync(a.alignment + static_cast<size_t>(step) * B * T, d_align, 4ul * B * T,
+                              cudaMemcpyDeviceToHost, s));
+      c.d2h_bytes += 4ul * B * T;
+    }
+    {
+      QuantOuts q = qouts();
+      qadd(q, xq[0], m.dec[0].rnn_wf.aq), qadd(q, xq[1], m.dec[0].rnn_w.aq);
+      launch_finalize_step(best, d_sl, d_forced, step, d_steps, done, tgt_len, counters, m.emb_q, m.inv_qm, m.sqrt_e,
+                           m.pos, B, E, xd, q, s);
+      c.launches++;
+    }
+    executed = step + 1;
+    // Model.cc:161: the loop stops once every sentence has produced EOS.  Poll the device counter
+    // every few steps (one 4-byte read) rather than synchronising each step.
+    if ((step & 3) == 3 || step + 1 == max_steps) {
+      SB_CUDA(cudaMemcpyAsync(&host_done, counters, 4, cudaMemcpyDeviceToHost, s));
+      SB_CUDA(cudaStreamSynchronize(s));
+      c.d2h_bytes += 4;
+      if (host_done >= B) break;
+    }
+  }
+
+  // ---- results
+  std::vector<uint32_t> lens(B);
+  SB_CUDA(cudaMemcpyAsync(lens.data(), tgt_len, 4ul * B, cudaMemcpyDeviceToHost, s));
+  if (!a.device_io && a.step_tokens && executed > 0) {
+    SB_CUDA(cudaMemcpyAsync(a.step_tokens, d_steps, 4ul * executed * B, cudaMemcpyDeviceToHost, s));
+    c.d2h_bytes += 4ul * executed * B;
+  }
+  SB_CUDA(cudaStreamSynchronize(s));
+  c.d2h_bytes += 4ul * B;
+  uint64_t total = 0;
+  uint32_t longest = 0;
+  bool all_done = host_done >= B;
+  for (int b = 0; b < B; b++) {
+    total += lens[b];
+    longest = std::max(longest, lens[b]);
+  }
+  a.target_tokens = total;
+  // steps the reference would have run: up to the step where the last sentence finished
+  a.steps = all_done ? longest : static_cast<size_t>(executed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error(std::string("forward failed: ") + cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+}  // namespace sb

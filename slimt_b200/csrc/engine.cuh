@@ -1,0 +1,141 @@
+// Host-side engine: device context, model upload, and the orchestration of
+// Model::forward (reference slimt/Model.cc:111-204) as a sequence of the
+// kernels in gemm_i8.cu / kernels.cu on one CUDA stream.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "gemm_i8.cuh"
+#include "kernels.cuh"
+
+namespace sb {
+
+void set_error(const std::string& msg);
+const char* last_error();
+
+#define SB_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      sb::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                   \
+      return 1;                                                                            \
+    }                                                                                      \
+  } while (0)
+
+struct Context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // cuTensorMapEncodeTiled, fetched through the runtime so libcuda is not a link-time dependency
+  CUresult (*encode_tiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
+  // workspace arena (grown on demand, reused across calls)
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  size_t arena_used = 0;
+  char* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+  uint64_t launches = 0;
+  uint64_t h2d_bytes = 0, d2h_bytes = 0;
+
+  int init(int dev);
+  void destroy();
+  int reserve(size_t bytes);
+  template <class T>
+  T* take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(arena + arena_used);
+    arena_used += bytes;
+    return p;
+  }
+  // int8 row-major [rows][cols] -> 2D tensor map, box = {128 bytes, box_rows}, 128B swizzle
+  int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
+};
+
+// One int8 weight matrix on the device, with everything the epilogue needs precomputed at load
+// (the reference recomputes PrepareBias on every call: qmm/Intgemm.inl.cc:112-128).
+struct DevWeight {
+  int K = 0, N = 0;
+  float aq = 0, bq = 0, um = 0;
+  int8_t* w = nullptr;      // [N][K]
+  int32_t* c127 = nullptr;  // [N]
+  float* pb = nullptr;      // [N]
+};
+
+struct DevLN {
+  float* scale = nullptr;
+  float* bias = nullptr;
+};
+
+struct AttnW {
+  DevWeight q, k, v, o;
+  DevLN ln;
+};
+struct FfnW {
+  DevWeight w1, w2;
+  DevLN ln;
+};
+struct EncLayerW {
+  AttnW self;
+  FfnW ffn;
+};
+struct DecLayerW {
+  DevWeight rnn_w, rnn_wf;
+  DevLN rnn_ln;
+  AttnW ctx;
+  FfnW ffn;
+};
+
+struct Model {
+  Context* ctx = nullptr;
+  int E = 0, F = 0, V = 0, H = 8, dh = 32;
+  std::vector<EncLayerW> enc;
+  std::vector<DecLayerW> dec;
+  int8_t* emb_q = nullptr;  // [V][E] stored embedding (lookup: float(q) * (1/qm), Io.cc:275-283)
+  float emb_qm = 0, inv_qm = 0, sqrt_e = 0;
+  DevWeight out;            // Wemb_intgemm8 (re-quantised embedding) + decoder_ff_logit_out_b + none_QuantMultA
+  float* pos = nullptr;     // sinusoidal table [max_pos][E]
+  int max_pos = 0;
+  std::vector<void*> owned;
+
+  int load(Context* c, const void* bin, size_t bytes, int enc_layers, int dec_layers, int heads);
+  void destroy();
+};
+
+struct ForwardArgs {
+  const uint32_t* tokens = nullptr;
+  const uint32_t* lengths = nullptr;
+  size_t B = 0, T = 0;
+  float limit_factor = 1.5f;
+  const uint32_t* shortlist = nullptr;
+  size_t n_shortlist = 0;
+  const uint32_t* forced = nullptr;
+  bool device_io = false;
+  uint32_t* step_tokens = nullptr;
+  size_t steps = 0;
+  uint64_t target_tokens = 0;
+  float* encoder_out = nullptr;
+  float* logits = nullptr;
+  float* alignment = nullptr;
+};
+
+int model_forward(Model& m, ForwardArgs& a);
+
+// qmm::affine family on host buffers (operator-level drop-in + parity taps)
+int qmm_affine_host(Context& c, const float* x, size_t M, size_t K, const int8_t* W, size_t N, const float* bias,
+                    float aq, float bq, const uint32_t* indices, size_t n_idx, float* y, int8_t* qa_out,
+                    int32_t* acc_out);
+
+// Host-side exact helpers shared by loader and operator API
+void host_prepare_bias(const int8_t* Bt, const float* bias, float aq, float bq, size_t K, size_t N, float* pb,
+                       int32_t* c127);
+void host_quantize(const float* x, int8_t* q, float mult, size_t n);
+
+}  // namespace sb

@@ -1,0 +1,430 @@
+// See kernels.cuh.  sm_100a; compiled with -fmad=false, all f32 arithmetic spelled with explicit
+// round-to-nearest intrinsics in the reference's evaluation order.
+#include "kernels.cuh"
+
+#include <stdio.h>
+
+#include "exact_math.cuh"
+
+namespace sb {
+
+namespace {
+
+__device__ __forceinline__ void store_quant4(const QuantOuts& q, size_t off, const float (&y)[4]) {
+  for (int k = 0; k < q.n; k++) {
+    const float aq = q.aq[k];
+    *reinterpret_cast<uint32_t*>(q.ptr[k] + off) =
+        pack4(quantize1(y[0], aq), quantize1(y[1], aq), quantize1(y[2], aq), quantize1(y[3], aq));
+  }
+}
+
+// ------------------------------------------------------------------ embedding
+__global__ void embed_kernel(const uint32_t* __restrict__ tokens, const int8_t* __restrict__ emb_q, float inv_qm,
+                             float sqrt_e, const float* __restrict__ pos, int rows, int T, int E, int pos_from_row,
+                             int zero_embed, float* __restrict__ x, QuantOuts q) {
+  const int per_row = E >> 2;
+  const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<size_t>(rows) * per_row) return;
+  const int r = static_cast<int>(gid / per_row);
+  const int e = static_cast<int>(gid % per_row) * 4;
+  float w[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (!zero_embed) {
+    const uint32_t tok = tokens[r];
+    const char4 c = *reinterpret_cast<const char4*>(emb_q + static_cast<size_t>(tok) * E + e);
+    w[0] = __fmul_rn(static_cast<float>(c.x), inv_qm);
+    w[1] = __fmul_rn(static_cast<float>(c.y), inv_qm);
+    w[2] = __fmul_rn(static_cast<float>(c.z), inv_qm);
+    w[3] = __fmul_rn(static_cast<float>(c.w), inv_qm);
+  }
+  const int p = pos_from_row ? (r % T) : 0;
+  const float4 ps = *reinterpret_cast<const float4*>(pos + static_cast<size_t>(p) * E + e);
+  float y[4];
+  y[0] = __fadd_rn(__fmul_rn(w[0], sqrt_e), ps.x);
+  y[1] = __fadd_rn(__fmul_rn(w[1], sqrt_e), ps.y);
+  y[2] = __fadd_rn(__fmul_rn(w[2], sqrt_e), ps.z);
+  y[3] = __fadd_rn(__fmul_rn(w[3], sqrt_e), ps.w);
+  const size_t off = static_cast<size_t>(r) * E + e;
+  if (x) *reinterpret_cast<float4*>(x + off) = make_float4(y[0], y[1], y[2], y[3]);
+  store_quant4(q, off, y);
+}
+
+__global__ void quantize_kernel(const float* __restrict__ x, size_t n4, QuantOuts q) {
+  const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(x)[gid];
+  const float y[4] = {v.x, v.y, v.z, v.w};
+  store_quant4(q, gid * 4, y);
+}
+
+// ------------------------------------------------------------------ self attention
+// Block = one (sentence, head); thread = one query row.  K and V of the head sit in shared memory and are
+// read as warp broadcasts; every dot product is a sequential fmaf chain (ruy's sgemm order), the
+// softmax max/sum/divide follow slimt/TensorOps.cc:282-315.
+template <int DH>
+__global__ void self_attention_kernel(const float* __restrict__ Q, const float* __restrict__ K,
+                                      const float* __restrict__ V, const uint32_t* __restrict__ lengths, int T,
+                                      int H, float dk, float* __restrict__ out_f32, QuantOuts q) {
+  extern __shared__ float smem_f[];
+  const int b = blockIdx.x / H;
+  const int h = blockIdx.x % H;
+  const int E = H * DH;
+  const int len = min(static_cast<int>(lengths[b]), T);
+  const int Tp = T | 1;
+  float* Ks = smem_f;
+  float* Vs = Ks + static_cast<size_t>(T) * DH;
+  float* Ss = Vs + static_cast<size_t>(T) * DH;
+
+  const size_t base = static_cast<size_t>(b) * T * E + static_cast<size_t>(h) * DH;
+  for (int i = threadIdx.x; i < len * (DH / 4); i += blockDim.x) {
+    const int j = i / (DH / 4);
+    const int c = (i % (DH / 4)) * 4;
+    *reinterpret_cast<float4*>(Ks + j * DH + c) = *reinterpret_cast<const float4*>(K + base + static_cast<size_t>(j) * E + c);
+    *reinterpret_cast<float4*>(Vs + j * DH + c) = *reinterpret_cast<const float4*>(V + base + static_cast<size_t>(j) * E + c);
+  }
+  __syncthreads();
+
+  float* S = Ss + static_cast<size_t>(threadIdx.x) * Tp;
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    float acc[DH];
+    const size_t off = base + static_cast<size_t>(i) * E;
+    if (i < len) {
+      float qv[DH];
+#pragma unroll
+      for (int d = 0; d < DH; d += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(Q + off + d);
+        qv[d] = t.x, qv[d + 1] = t.y, qv[d + 2] = t.z, qv[d + 3] = t.w;
+      }
+      float mx = -3.402823466e+38f;
+      for (int j = 0; j < len; j++) {
+        float s = 0.0f;
+#pragma unroll
+        for (int d = 0; d < DH; d++) s = fmaf(qv[d], Ks[j * DH + d], s);
+        s = __fmul_rn(dk, s);
+        S[j] = s;
+        mx = fmaxf(mx, s);
+      }
+      float sum = 0.0f;
+      for (int j = 0; j < len; j++) {
+        const float e = expf_glibc(__fsub_rn(S[j], mx));
+        S[j] = e;
+        sum = __fadd_rn(sum, e);
+      }
+#pragma unroll
+      for (int d = 0; d < DH; d++) acc[d] = 0.0f;
+      for (int j = 0; j < len; j++) {
+        const float p = __fdiv_rn(S[j], sum);
+#pragma unroll
+        for (int d = 0; d < DH; d++) acc[d] = fmaf(p, Vs[j * DH + d], acc[d]);
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < DH; d++) acc[d] = 0.0f;  // padded query rows never reach a valid output
+    }
+    if (out_f32) {
+#pragma unroll
+      for (int d = 0; d < DH; d += 4) *reinterpret_cast<float4*>(out_f32 + off + d) = make_float4(acc[d], acc[d + 1], acc[d + 2], acc[d + 3]);
+    }
+#pragma unroll
+    for (int d = 0; d < DH; d += 4) {
+      const float y[4] = {acc[d], acc[d + 1], acc[d + 2], acc[d + 3]};
+      store_quant4(q, off + d, y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ cross attention (decode)
+// Warp = one (sentence, head), one query.  Lane j scores key j (+32, +64 ...), the sum runs in key
+// order through shuffles, lane d accumulates output dim d over keys in order (coalesced V reads).
+constexpr int kMaxKeyRegs = 8;  // S <= 256
+
+template <int DH>
+__global__ void cross_attention_kernel(const float* __restrict__ Qr, const float* __restrict__ Kc,
+                                       const float* __restrict__ Vc, const uint32_t* __restrict__ lengths, int B,
+                                       int S, int H, float dk, float* __restrict__ out_f32, QuantOuts q,
+                                       float* __restrict__ attn_head0) {
+  extern __shared__ float smem_f[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int gw = blockIdx.x * wpb + warp;
+  if (gw >= B * H) return;
+  const int b = gw / H, h = gw % H;
+  const int E = H * DH;
+  const int len = min(static_cast<int>(lengths[b]), S);
+  float* sq = smem_f + warp * DH;
+  const float* qrow = Qr + static_cast<size_t>(b) * E + h * DH;
+  for (int d = lane; d < DH; d += 32) sq[d] = qrow[d];
+  __syncwarp();
+
+  const size_t kv_base = static_cast<size_t>(b) * S * E + static_cast<size_t>(h) * DH;
+  float sc[kMaxKeyRegs];
+  float mx = -3.402823466e+38f;
+#pragma unroll
+  for (int m = 0; m < kMaxKeyRegs; m++) {
+    const int j = m * 32 + lane;
+    sc[m] = 0.0f;
+    if (j < len) {
+      const float* kr = Kc + kv_base + static_cast<size_t>(j) * E;
+      float s = 0.0f;
+#pragma unroll
+      for (int d = 0; d < DH; d += 4) {
+        const float4 kk = *reinterpret_cast<const float4*>(kr + d);
+        s = fmaf(sq[d], kk.x, s);
+        s = fmaf(sq[d + 1], kk.y, s);
+        s = fmaf(sq[d + 2], kk.z, s);
+        s = fmaf(sq[d + 3], kk.w, s);
+      }
+      s = __fmul_rn(dk, s);
+      sc[m] = s;
+      mx = fmaxf(mx, s);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+#pragma unroll
+  for (int m = 0; m < kMaxKeyRegs; m++) {
+    const int j = m * 32 + lane;
+    sc[m] = (j < len) ? expf_glibc(__fsub_rn(sc[m], mx)) : 0.0f;
+  }
+  float sum = 0.0f;
+#pragma unroll
+  for (int m = 0; m < kMaxKeyRegs; m++) {
+    if (m * 32 < len) {
+      const int lim = min(32, len - m * 32);
+      for (int l = 0; l < lim; l++) sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, sc[m], l));
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < kMaxKeyRegs; m++) sc[m] = __fdiv_rn(sc[m], sum);
+  if (attn_head0 != nullptr && h == 0) {
+#pragma unroll
+    for (int m = 0; m < kMaxKeyRegs; m++) {
+      const int j = m * 32 + lane;
+      if (j < S) attn_head0[static_cast<size_t>(b) * S + j] = (j < len) ? sc[m] : 0.0f;
+    }
+  }
+  float acc[DH / 32];
+#pragma unroll
+  for (int u = 0; u < DH / 32; u++) acc[u] = 0.0f;
+#pragma unroll
+  for (int m = 0; m < kMaxKeyRegs; m++) {
+    if (m * 32 < len) {
+      const int lim = min(32, len - m * 32);
+      for (int l = 0; l < lim; l++) {
+        const float p = __shfl_sync(0xffffffffu, sc[m], l);
+        const float* vr = Vc + kv_base + static_cast<size_t>(m * 32 + l) * E;
+#pragma unroll
+        for (int u = 0; u < DH / 32; u++) acc[u] = fmaf(p, vr[u * 32 + lane], acc[u]);
+      }
+    }
+  }
+  const size_t off = static_cast<size_t>(b) * E + h * DH;
+#pragma unroll
+  for (int u = 0; u < DH / 32; u++) {
+    if (out_f32) out_f32[off + u * 32 + lane] = acc[u];
+    for (int k = 0; k < q.n; k++) q.ptr[k][off + u * 32 + lane] = static_cast<int8_t>(quantize1(acc[u], q.aq[k]));
+  }
+}
+
+// ------------------------------------------------------------------ SSRU tail
+// Warp = one sentence row.  Elementwise part is lane-parallel and coalesced; the two LayerNorm sums
+// run in element order over the row parked in shared memory (every lane walks the same chain).
+__global__ void ssru_ln_kernel(const float* __restrict__ f, const float* __restrict__ wx, float* __restrict__ state,
+                               const float* __restrict__ x, const float* __restrict__ ln_scale,
+                               const float* __restrict__ ln_bias, float eps, int B, int E, float* __restrict__ h,
+                               QuantOuts q) {
+  extern __shared__ float smem_f[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= B) return;
+  float* t = smem_f + static_cast<size_t>(warp) * E;
+  const size_t base = static_cast<size_t>(row) * E;
+  for (int e = lane; e < E; e += 32) {
+    const float sg = sigmoid_ref(f[base + e]);
+    const float a = __fmul_rn(sg, state[base + e]);
+    const float bb = __fmul_rn(__fsub_rn(1.0f, sg), wx[base + e]);
+    const float c = __fadd_rn(a, bb);  // highway(c_prev, Wx, f), slimt/TensorOps.cc:662-682
+    state[base + e] = c;
+    const float y = c > 0.0f ? c : 0.0f;
+    t[e] = __fadd_rn(x[base + e], y);
+  }
+  __syncwarp();
+  float sum = 0.0f;
+  for (int e = 0; e < E; e++) sum = __fadd_rn(sum, t[e]);
+  const float cols = static_cast<float>(E);
+  const float mean = __fdiv_rn(sum, cols);
+  float sq = 0.0f;
+  for (int e = 0; e < E; e++) {
+    const float d = __fsub_rn(t[e], mean);
+    sq = __fadd_rn(sq, __fmul_rn(d, d));
+  }
+  const float sigma = __fsqrt_rn(__fadd_rn(__fdiv_rn(sq, cols), eps));
+  for (int e = lane; e < E; e += 32) {
+    const float n = __fdiv_rn(__fsub_rn(t[e], mean), sigma);
+    const float y = __fadd_rn(__fmul_rn(ln_scale[e], n), ln_bias[e]);
+    if (h) h[base + e] = y;
+    for (int k = 0; k < q.n; k++) q.ptr[k][base + e] = static_cast<int8_t>(quantize1(y, q.aq[k]));
+  }
+}
+
+// ------------------------------------------------------------------ step bookkeeping
+__global__ void finalize_step_kernel(unsigned long long* __restrict__ best, const uint32_t* __restrict__ shortlist,
+                                     const uint32_t* __restrict__ forced, int step, uint32_t* __restrict__ step_tokens,
+                                     uint8_t* __restrict__ done, uint32_t* __restrict__ tgt_len,
+                                     int* __restrict__ n_done,
+                                     const int8_t* __restrict__ emb_q, float inv_qm, float sqrt_e,
+                                     const float* __restrict__ pos0, int B, int E, float* __restrict__ x, QuantOuts q) {
+  __shared__ uint32_t s_next;
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    const unsigned long long packed = best[b];
+    const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(packed & 0xFFFFFFFFull);
+    const uint32_t word = shortlist ? shortlist[idx] : idx;
+    step_tokens[static_cast<size_t>(step) * B + b] = word;
+    if (!done[b]) {  // record(), slimt/Model.cc:127-137: append unless already finished; EOS id is 0
+      tgt_len[b] += 1;
+      if (word == 0u) {
+        done[b] = 1;
+        atomicAdd(n_done, 1);
+      }
+    }
+    best[b] = 0ull;
+    s_next = forced ? forced[static_cast<size_t>(step) * B + b] : word;
+  }
+  __syncthreads();
+  const uint32_t tok = s_next;
+  for (int e = threadIdx.x * 4; e < E; e += blockDim.x * 4) {
+    const char4 c = *reinterpret_cast<const char4*>(emb_q + static_cast<size_t>(tok) * E + e);
+    const float4 ps = *reinterpret_cast<const float4*>(pos0 + e);
+    float y[4];
+    y[0] = __fadd_rn(__fmul_rn(__fmul_rn(static_cast<float>(c.x), inv_qm), sqrt_e), ps.x);
+    y[1] = __fadd_rn(__fmul_rn(__fmul_rn(static_cast<float>(c.y), inv_qm), sqrt_e), ps.y);
+    y[2] = __fadd_rn(__fmul_rn(__fmul_rn(static_cast<float>(c.z), inv_qm), sqrt_e), ps.z);
+    y[3] = __fadd_rn(__fmul_rn(__fmul_rn(static_cast<float>(c.w), inv_qm), sqrt_e), ps.w);
+    const size_t off = static_cast<size_t>(b) * E + e;
+    *reinterpret_cast<float4*>(x + off) = make_float4(y[0], y[1], y[2], y[3]);
+    store_quant4(q, off, y);
+  }
+}
+
+__global__ void gather_rows_kernel(const int8_t* __restrict__ W, const float* __restrict__ pb,
+                                   const int32_t* __restrict__ c127, const uint32_t* __restrict__ idx, int K,
+                                   int8_t* __restrict__ W_sel, float* __restrict__ pb_sel, int32_t* __restrict__ c127_sel) {
+  const int i = blockIdx.x;
+  const uint32_t src = idx[i];
+  const uint4* s = reinterpret_cast<const uint4*>(W + static_cast<size_t>(src) * K);
+  uint4* d = reinterpret_cast<uint4*>(W_sel + static_cast<size_t>(i) * K);
+  for (int t = threadIdx.x; t < K / 16; t += blockDim.x) d[t] = s[t];
+  if (threadIdx.x == 0) {
+    pb_sel[i] = pb[src];
+    c127_sel[i] = c127[src];
+  }
+}
+
+__device__ __forceinline__ unsigned long long pack_best_k(float v, uint32_t idx) {
+  if (v == 0.0f) v = 0.0f;
+  uint32_t bits = __float_as_uint(v);
+  uint32_t key = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+  return (static_cast<unsigned long long>(key) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - idx);
+}
+
+__global__ void argmax_rows_kernel(const float* __restrict__ logits, int cols, unsigned long long* __restrict__ best) {
+  const int row = blockIdx.x;
+  const float* p = logits + static_cast<size_t>(row) * cols;
+  unsigned long long loc = 0ull;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const unsigned long long k = pack_best_k(p[c], c);
+    loc = k > loc ? k : loc;
+  }
+  atomicMax(best + row, loc);
+}
+
+}  // namespace
+
+void launch_embed(const uint32_t* tokens, const int8_t* emb_q, float inv_qm, float sqrt_e, const float* pos, int rows,
+                  int T, int E, int pos_from_row, int zero_embed, float* x, QuantOuts q, cudaStream_t stream) {
+  const size_t n = static_cast<size_t>(rows) * (E / 4);
+  if (n == 0) return;
+  embed_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(tokens, emb_q, inv_qm, sqrt_e, pos, rows, T, E,
+                                                                         pos_from_row, zero_embed, x, q);
+}
+
+void launch_quantize(const float* x, size_t n, QuantOuts q, cudaStream_t stream) {
+  const size_t n4 = n / 4;
+  if (n4 == 0) return;
+  quantize_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(x, n4, q);
+}
+
+void launch_self_attention(const float* Q, const float* K, const float* V, const uint32_t* lengths, int B, int T, int H,
+                           int dh, float* out_f32, QuantOuts q, cudaStream_t stream) {
+  if (B == 0) return;
+  // 1/sqrt(dim_head) evaluated in double then narrowed, as `1.0F / std::sqrt(size_t)` does (Modules.cc:43).
+  const float dk = static_cast<float>(1.0 / std::sqrt(static_cast<double>(dh)));
+  int threads = ((T + 31) / 32) * 32;
+  if (threads > 128) threads = 128;
+  const int Tp = T | 1;
+  size_t smem = (static_cast<size_t>(2) * T * dh + static_cast<size_t>(threads) * Tp) * sizeof(float);
+  while (smem > 200 * 1024 && threads > 32) {
+    threads -= 32;
+    smem = (static_cast<size_t>(2) * T * dh + static_cast<size_t>(threads) * Tp) * sizeof(float);
+  }
+  if (dh == 32) {
+    cudaFuncSetAttribute(self_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    self_attention_kernel<32><<<B * H, threads, smem, stream>>>(Q, K, V, lengths, T, H, dk, out_f32, q);
+  } else if (dh == 64) {
+    cudaFuncSetAttribute(self_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    self_attention_kernel<64><<<B * H, threads, smem, stream>>>(Q, K, V, lengths, T, H, dk, out_f32, q);
+  } else {
+    fprintf(stderr, "slimt_b200: unsupported head dim %d\n", dh);
+    abort();
+  }
+}
+
+void launch_cross_attention(const float* Qr, const float* Kc, const float* Vc, const uint32_t* lengths, int B, int S,
+                            int H, int dh, float* out_f32, QuantOuts q, float* attn_head0, cudaStream_t stream) {
+  if (B == 0) return;
+  if (S > 32 * kMaxKeyRegs) {
+    fprintf(stderr, "slimt_b200: source length %d exceeds %d\n", S, 32 * kMaxKeyRegs);
+    abort();
+  }
+  const float dk = static_cast<float>(1.0 / std::sqrt(static_cast<double>(dh)));
+  const int wpb = 8;
+  const int blocks = (B * H + wpb - 1) / wpb;
+  const size_t smem = static_cast<size_t>(wpb) * dh * sizeof(float);
+  if (dh == 32) {
+    cross_attention_kernel<32><<<blocks, wpb * 32, smem, stream>>>(Qr, Kc, Vc, lengths, B, S, H, dk, out_f32, q, attn_head0);
+  } else if (dh == 64) {
+    cross_attention_kernel<64><<<blocks, wpb * 32, smem, stream>>>(Qr, Kc, Vc, lengths, B, S, H, dk, out_f32, q, attn_head0);
+  } else {
+    fprintf(stderr, "slimt_b200: unsupported head dim %d\n", dh);
+    abort();
+  }
+}
+
+void launch_ssru_ln(const float* f, const float* wx, float* state, const float* x, const float* ln_scale,
+                    const float* ln_bias, float eps, int B, int E, float* h, QuantOuts q, cudaStream_t stream) {
+  if (B == 0) return;
+  const int wpb = 4;
+  const size_t smem = static_cast<size_t>(wpb) * E * sizeof(float);
+  ssru_ln_kernel<<<(B + wpb - 1) / wpb, wpb * 32, smem, stream>>>(f, wx, state, x, ln_scale, ln_bias, eps, B, E, h, q);
+}
+
+void launch_finalize_step(unsigned long long* best, const uint32_t* shortlist, const uint32_t* forced, int step,
+                          uint32_t* step_tokens, uint8_t* done, uint32_t* tgt_len, int* n_done, const int8_t* emb_q, float inv_qm,
+                          float sqrt_e, const float* pos0, int B, int E, float* x, QuantOuts q, cudaStream_t stream) {
+  if (B == 0) return;
+  finalize_step_kernel<<<B, 64, 0, stream>>>(best, shortlist, forced, step, step_tokens, done, tgt_len, n_done, emb_q, inv_qm,
+                                             sqrt_e, pos0, B, E, x, q);
+}
+
+void launch_gather_rows(const int8_t* W, const float* pb, const int32_t* c127, const uint32_t* idx, int n_idx, int K,
+                        int8_t* W_sel, float* pb_sel, int32_t* c127_sel, cudaStream_t stream) {
+  if (n_idx == 0) return;
+  gather_rows_kernel<<<n_idx, 32, 0, stream>>>(W, pb, c127, idx, K, W_sel, pb_sel, c127_sel);
+}
+
+void launch_argmax_rows(const float* logits, int rows, int cols, unsigned long long* best, cudaStream_t stream) {
+  if (rows == 0) return;
+  argmax_rows_kernel<<<rows, 256, 0, stream>>>(logits, cols, best);
+}
+
+}  // namespace sb

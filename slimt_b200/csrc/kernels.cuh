@@ -1,0 +1,57 @@
+// Non-GEMM kernels of the hot path (embedding, attention, SSRU, step bookkeeping).
+// Each one reproduces the reference's f32 arithmetic bit for bit (see
+// exact_math.cuh) while emitting the int8 operands of the GEMMs that consume it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb {
+
+constexpr int kMaxQ = 4;
+
+struct QuantOuts {
+  int8_t* ptr[kMaxQ];
+  float aq[kMaxQ];
+  int n;
+};
+
+// x[r] = float(emb_q[tok[r]]) * inv_qm * sqrt_e + pos[(r % T) or 0]   (index_select + transform_embedding,
+// slimt/TensorOps.cc:227-243, Transformer.cc:24-49, Io.cc:275-283).  zero_embed=1 is decoder step 0.
+void launch_embed(const uint32_t* tokens, const int8_t* emb_q, float inv_qm, float sqrt_e, const float* pos,
+                  int rows, int T, int E, int pos_from_row, int zero_embed, float* x, QuantOuts q,
+                  cudaStream_t stream);
+
+// f32 -> int8 copies (PrepareA as a standalone op, for the qmm:: operator API).
+void launch_quantize(const float* x, size_t n, QuantOuts q, cudaStream_t stream);
+
+// Encoder self-attention on unsplit [B*T][E] Q,K,V (scaled_dot_product_attention, slimt/Modules.cc:24-86,
+// with split_heads/join_heads folded into the addressing).  Emits the Wo operand (int8) and/or f32.
+void launch_self_attention(const float* Q, const float* K, const float* V, const uint32_t* lengths, int B, int T,
+                           int H, int dh, float* out_f32, QuantOuts q, cudaStream_t stream);
+
+// Decoder cross-attention for one query row per sentence over cached K,V [B][S][E].
+// attn_head0 (optional) receives head 0's probabilities [B][S] (alignment, slimt/Model.cc:84-108).
+void launch_cross_attention(const float* Qr, const float* Kc, const float* Vc, const uint32_t* lengths, int B,
+                            int S, int H, int dh, float* out_f32, QuantOuts q, float* attn_head0,
+                            cudaStream_t stream);
+
+// SSRU cell tail (slimt/Modules.cc:190-235): c = highway(c_prev, Wx, f); h = LN(x + relu(c)); state <- c.
+void launch_ssru_ln(const float* f, const float* wx, float* state, const float* x, const float* ln_scale,
+                    const float* ln_bias, float eps, int B, int E, float* h, QuantOuts q, cudaStream_t stream);
+
+// Per decode step: packed argmax -> word id (through the shortlist when given), record into
+// step_tokens[step][B], EOS bookkeeping, re-arm `best`, and build the next step's decoder input
+// (embedding * sqrt(E) + position-0 signal; quirk Q1) with its int8 copies.
+void launch_finalize_step(unsigned long long* best, const uint32_t* shortlist, const uint32_t* forced, int step,
+                          uint32_t* step_tokens, uint8_t* done, uint32_t* tgt_len, int* n_done, const int8_t* emb_q, float inv_qm,
+                          float sqrt_e, const float* pos0, int B, int E, float* x, QuantOuts q,
+                          cudaStream_t stream);
+
+// Shortlist: gather rows of the output weight and its prepared bias / shift terms.
+void launch_gather_rows(const int8_t* W, const float* pb, const int32_t* c127, const uint32_t* idx, int n_idx,
+                        int K, int8_t* W_sel, float* pb_sel, int32_t* c127_sel, cudaStream_t stream);
+
+// Row-wise first-max over f32 logits (used when logits are materialised for parity taps).
+void launch_argmax_rows(const float* logits, int rows, int cols, unsigned long long* best, cudaStream_t stream);
+
+}  // namespace sb
