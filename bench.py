@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json: target tokens/sec, greedy, tiny11 int8).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path (oracle/_ref) on host cores
+
+A "step" is one pass of Model::forward over one batch stream of synthetic input: configs[1] of
+BASELINE.json -- tiny11-shaped int8 random-init model with a lexical shortlist, 4096 sentences of 32 tokens
+per GPU (weak scaling: every rank owns its own 4096 sentences; sentences are independent, no collective).
+
+Printed JSON (rank 0): `value` = whole-job target tokens/s with the batch resident in HBM (device-timed,
+max over ranks); `e2e` = the same metric through the C-ABI call a user makes (slimt_b200_translate: host
+buffers, Batcher + shortlist generation on the host, H2D/D2H inside the timed region); `roofline` for the
+dominant kernel from per-kernel CUDA-event timings of one extra (untimed) profiled pass; `cpu_baseline`
+= the reference compiled in place (oracle/_ref) timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from slimt_b200 import synth  # noqa: E402
+
+SENTENCES_PER_GPU = 4096
+SRC_LEN = 32
+LIMIT = 1.5
+MODEL_SEED = 1234
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "slimt_ref")
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_assets(tmp: str, rank: int):
+    model_path = os.path.join(tmp, "tiny11.bin")
+    synth.write_model(model_path, synth.make_params(synth.TINY, seed=MODEL_SEED))
+    fr, offs, lists = synth.make_shortlist(vocab=synth.TINY.vocab, frequent=100, best=100, seed=7)
+    sl_path = os.path.join(tmp, "lex.s2t.bin")
+    synth.write_shortlist(sl_path, fr, offs, lists, best=100)
+    sentences = synth.make_sentences(SENTENCES_PER_GPU, SRC_LEN, vocab=synth.TINY.vocab, seed=1000 + rank)
+    return model_path, sl_path, (fr, offs, lists), sentences
+
+
+def cpu_reference_run(model_path, shortlist, sentences, workers, batch_sentences=64, repeats=1):
+    """Times oracle/_ref/slimt_ref (the unmodified reference, intgemm provider) on `workers` host threads."""
+    from oracle import slimt_oracle as so
+    fr, offs, lists = shortlist
+    nb = max(1, len(sentences) // batch_sentences)
+    recs = []
+    for b in range(nb):
+        chunk = sentences[b * batch_sentences:(b + 1) * batch_sentences]
+        words = np.concatenate(chunk)
+        sl = so.shortlist_generate(words, fr, offs, lists, synth.TINY.vocab)
+        recs.append(synth.pack_batch(chunk, LIMIT, sl))
+    with tempfile.NamedTemporaryFile(suffix=".batches", delete=False) as f:
+        f.write(np.uint32(len(recs)).tobytes() + b"".join(recs))
+        path = f.name
+    try:
+        out = subprocess.run([REF_BIN, "bench", "--model", model_path, "--batches", path, "--workers", str(workers),
+                              "--repeat", str(repeats)], capture_output=True, text=True, check=True).stdout
+    finally:
+        os.unlink(path)
+    lines = [json.loads(l) for l in out.strip().splitlines()]
+    return lines
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    tmp = tempfile.mkdtemp(prefix="slimt_b200_ref_")
+    model_path, _, shortlist, sentences = build_assets(tmp, 0)
+    if not os.path.exists(REF_BIN):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/slimt_ref not built (needs /root/reference)"}))
+        return 0
+    # Each step is a bounded sample of the workload: one 64-sentence batch per host thread.
+    sample = sentences[:64 * cores]
+    lines = cpu_reference_run(model_path, shortlist, sample, cores, repeats=args.warmup + args.steps)
+    timed = lines[args.warmup:]
+    secs = sum(l["seconds"] for l in timed)
+    toks = sum(l["target_tokens"] for l in timed)
+    value = toks / secs
+    sample_desc = f"{len(sample)} of {SENTENCES_PER_GPU} sentences x {SRC_LEN} tokens per step, 64-sentence batches, one per thread"
+    print(json.dumps({
+        "impl": "reference", "metric": "target_tokens_per_sec", "value": value, "unit": "tokens/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(timed)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cores, "kind": "reference", "sample": sample_desc},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+    return 0
+
+
+def workload_config():
+    return {"workload": "tiny11 int8 (emb 256, ffn 1536, 6 enc / 2 SSRU dec, vocab 32000, random-init seed 1234) "
+                        "with lexical shortlist, greedy decode of 4096 synthetic sentences x 32 tokens per GPU "
+                        "(BASELINE.json configs[1])",
+            "sentences_per_gpu": SENTENCES_PER_GPU, "src_len": SRC_LEN, "limit_factor": LIMIT,
+            "max_words": SENTENCES_PER_GPU * SRC_LEN, "l2": "flushed between timed steps (256 MiB memset)",
+            "sharding": "independent sentences per rank, no collective"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+
+    from slimt_b200 import capi
+    ctx = capi.Context(local_rank)  # raises without a GPU: no CPU fallback
+    tmp = tempfile.mkdtemp(prefix=f"slimt_b200_bench_{rank}_")
+    model_path, sl_path, shortlist, sentences = build_assets(tmp, rank)
+    model = capi.Model(ctx, open(model_path, "rb").read())
+    sl_bin = open(sl_path, "rb").read()
+    max_words = SENTENCES_PER_GPU * SRC_LEN
+
+    # ---- device-resident arm: the batches a Batcher would form, uploaded once
+    plan = capi.batcher_plan([len(s) for s in sentences], max_words)
+    resident = []
+    for ids, width in plan:
+        B = len(ids)
+        tok = np.zeros((B, width), dtype=np.uint32)
+        lens = np.zeros(B, dtype=np.uint32)
+        for r, i in enumerate(ids):
+            tok[r, :len(sentences[i])] = sentences[i]
+            lens[r] = len(sentences[i])
+        sl = capi.shortlist_generate(sl_bin, np.concatenate([sentences[i] for i in ids]), model.V)
+        max_steps = int(np.float32(LIMIT) * np.float32(width))
+        resident.append({"B": B, "T": width, "tok": ctx.to_device(tok), "lens": ctx.to_device(lens),
+                         "sl": ctx.to_device(sl), "nsl": len(sl), "steps": ctx.dev_alloc(4 * max_steps * B)})
+
+    def resident_pass():
+        toks = 0
+        for b in resident:
+            _, t = model.forward_resident(b["tok"], b["lens"], b["B"], b["T"], b["steps"], LIMIT, b["sl"], b["nsl"])
+            toks += t
+        return toks
+
+    def barrier():
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        resident_pass()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = ctx.launches()
+    step_ms, tokens_per_step = [], 0
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        ctx.timer_start()
+        tokens_per_step = resident_pass()
+        step_ms.append(ctx.timer_stop())
+    launches = ctx.launches() - launches0
+    barrier()
+    clocks = sampler.stop()
+    total_ms = sum(step_ms)
+
+    # ---- end-to-end arm through the public C-ABI call with host buffers
+    for _ in range(max(1, args.warmup - 1)):
+        model.translate(sentences, max_words, LIMIT, sl_bin)
+    barrier()
+    e2e_s, e2e_tokens, e2e_stats = 0.0, 0, None
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        _, st = model.translate(sentences, max_words, LIMIT, sl_bin)
+        e2e_s += time.perf_counter() - t0
+        e2e_tokens += st["target_tokens"]
+        e2e_stats = st
+    barrier()
+
+    # ---- per-kernel event timing: one extra profiled pass (not part of the timed region)
+    ctx.profile(True)
+    resident_pass()
+    stats = ctx.profile_read()
+    ctx.profile(False)
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0]), float(t[1])
+        n = torch.tensor([float(tokens_per_step * args.steps), float(e2e_tokens), float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+        all_tokens, all_e2e_tokens, all_launches = float(n[0]), float(n[1]), int(n[2])
+    else:
+        all_tokens, all_e2e_tokens, all_launches = float(tokens_per_step * args.steps), float(e2e_tokens), launches
+
+    if rank != 0:
+        return 0
+
+    peaks = measured_peaks()
+    int8_peak_tops = 2.0 * peaks["bf16_tflops"]  # int8 dense denominator = 2 x measured bf16
+    kern = []
+    tot_prof_ms = sum(s["ms"] for s in stats) or 1.0
+    for s in sorted(stats, key=lambda s: -s["ms"]):
+        sec = s["ms"] * 1e-3
+        entry = {"name": s["name"], "launches": s["launches"], "ms": round(s["ms"], 4), "share": round(s["ms"] / tot_prof_ms, 4),
+                 "avg_us": round(1e3 * s["ms"] / max(1, s["launches"]), 2)}
+        if s["ops"] > 0:
+            entry["tops"] = round(s["ops"] / sec / 1e12, 2)
+            entry["tensor_frac"] = round(s["ops"] / sec / 1e12 / int8_peak_tops, 4)
+        entry["gbs"] = round(s["bytes"] / sec / 1e9, 1)
+        entry["hbm_frac"] = round(s["bytes"] / sec / 1e9 / peaks["hbm_gbs"], 4)
+        kern.append(entry)
+    top = kern[0]
+    top_raw = next(s for s in stats if s["name"] == top["name"])
+    tensor_bound = top.get("tensor_frac", 0) > top["hbm_frac"]
+    if tensor_bound:
+        roof = {"kernel": top["name"], "bound": "tensor", "achieved": top["tops"], "peak": int8_peak_tops, "unit": "TOP/s",
+                "frac": top["tensor_frac"], "traffic": None,
+                "peak_source": f"2 x {peaks['source']} bf16 burst ({peaks['bf16_tflops']} TF/s), int8 dense"}
+    else:
+        roof = {"kernel": top["name"], "bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": top["hbm_frac"], "traffic": None, "peak_source": f"{peaks['source']} copy bandwidth"}
+    roof["algorithmic_per_launch"] = (top_raw["ops"] if tensor_bound else top_raw["bytes"]) / max(1, top_raw["launches"])
+    roof["avg_launch_us"] = top["avg_us"]
+    roof["share_of_step"] = top["share"]
+
+    out = {
+        "metric": "target_tokens_per_sec", "value": all_tokens / (total_ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic", "config": workload_config(),
+        "clocks": clocks,
+        "e2e": {"value": all_e2e_tokens / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": e2e_stats["h2d_bytes"],
+                "d2h_bytes_per_step": e2e_stats["d2h_bytes"], "api": "slimt_b200_translate (host buffers)"},
+        "gpu_launches": all_launches,
+        "roofline": roof,
+        "kernels": kern,
+        "target_tokens_per_step_per_gpu": tokens_per_step,
+        "batches_per_step": len(resident),
+    }
+
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        if os.path.exists(REF_BIN):
+            sample = sentences[:64 * cores]
+            lines = cpu_reference_run(model_path, shortlist, sample, cores, repeats=2)
+            best = max(l["target_tokens_per_s"] for l in lines)
+            out["cpu_baseline"] = {"value": best, "unit": "tokens/s", "cores": cores, "kind": "reference",
+                                   "sample": f"{len(sample)} of {SENTENCES_PER_GPU} sentences x {SRC_LEN} tokens, 64-sentence "
+                                             f"batches, one per host thread (intgemm provider, ruy sgemm), best of 2"}
+        else:
+            from oracle import slimt_oracle as so
+            fr, offs, lists = shortlist
+            chunk = sentences[:16]
+            tok = np.zeros((16, SRC_LEN), dtype=np.uint32)
+            for i, s in enumerate(chunk):
+                tok[i, :len(s)] = s
+            sl = so.shortlist_generate(np.concatenate(chunk), fr, offs, lists, synth.TINY.vocab)
+            orc = so.Oracle(synth.read_model(model_path))
+            t0 = time.perf_counter()
+            res = orc.forward(tok, np.array([len(s) for s in chunk]), LIMIT, shortlist=sl)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": sum(len(s) for s in res["sentences"]) / dt, "unit": "tokens/s", "cores": 1,
+                                   "kind": "port", "sample": "16 sentences x 32 tokens through oracle/slimt_oracle.py"}
+    print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

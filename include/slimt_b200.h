@@ -140,8 +140,29 @@ typedef struct slimt_b200_translate_io {
 
 int slimt_b200_translate(slimt_b200_model* model, slimt_b200_translate_io* io);
 
+/* Host-only pieces of the same path, callable without a GPU (used by the CPU test-suite):
+ * ShortlistGenerator::generate (Shortlist.cc:115-175) and Batcher::generate (Batcher.cc:95-120). */
+int slimt_b200_shortlist_generate(const void* shortlist_bin, size_t shortlist_bytes, const uint32_t* words,
+                                  size_t n_words, size_t vocab, uint32_t* out, size_t out_capacity, size_t* n_out);
+/* Writes sentence ids batch by batch into batch_ids [n] and the batch boundaries into
+ * batch_offsets [n_batches + 1] (capacity n + 1); widths [n_batches] receives each padded length. */
+int slimt_b200_batcher_plan(const uint64_t* lengths, size_t n, size_t max_words, uint64_t* batch_ids,
+                            uint64_t* batch_offsets, uint64_t* widths, size_t* n_batches);
+
 /* counters since context creation (bench.py reports gpu_launches from these) */
 uint64_t slimt_b200_kernel_launches(const slimt_b200_ctx* ctx);
+
+/* Per-kernel device timing: while enabled every launch on the context's stream is bracketed by
+ * CUDA events.  read() synchronises and aggregates by kernel tag, then clears the log. */
+typedef struct slimt_b200_kernel_stat {
+  char name[48];
+  uint64_t launches;
+  double ms;     /* sum of event-timed durations */
+  double ops;    /* algorithmic int8 operations (2*MAC) summed over launches */
+  double bytes;  /* algorithmic HBM bytes summed over launches */
+} slimt_b200_kernel_stat;
+int slimt_b200_profile_enable(slimt_b200_ctx* ctx, int on);
+int slimt_b200_profile_read(slimt_b200_ctx* ctx, slimt_b200_kernel_stat* out, size_t capacity, size_t* n_out);
 
 #ifdef __cplusplus
 }

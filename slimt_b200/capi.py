@@ -23,6 +23,7 @@ EXPORTS = [
     "slimt_b200_qmm_prepare_weight_quantized_transposed", "slimt_b200_qmm_prepare_weight_transposed",
     "slimt_b200_qmm_affine", "slimt_b200_qmm_affine_debug", "slimt_b200_model_create", "slimt_b200_model_destroy",
     "slimt_b200_model_dims", "slimt_b200_model_forward", "slimt_b200_translate", "slimt_b200_kernel_launches",
+    "slimt_b200_shortlist_generate", "slimt_b200_batcher_plan", "slimt_b200_profile_enable", "slimt_b200_profile_read",
 ]
 
 
@@ -46,6 +47,11 @@ class TranslateIO(C.Structure):
                 ("out_offsets", C.c_void_p), ("target_tokens", C.c_uint64), ("batches", C.c_uint64),
                 ("device_ms", C.c_double), ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64)]
+
+
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("launches", C.c_uint64), ("ms", C.c_double), ("ops", C.c_double),
+                ("bytes", C.c_double)]
 
 
 def lib() -> C.CDLL:
@@ -82,8 +88,38 @@ def lib() -> C.CDLL:
         L.slimt_b200_model_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.slimt_b200_model_forward.argtypes = [C.c_void_p, C.POINTER(ForwardIO)]
         L.slimt_b200_translate.argtypes = [C.c_void_p, C.POINTER(TranslateIO)]
+        L.slimt_b200_shortlist_generate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                                                    C.c_size_t, C.POINTER(C.c_size_t)]
+        L.slimt_b200_batcher_plan.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.POINTER(C.c_size_t)]
+        L.slimt_b200_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        L.slimt_b200_profile_read.argtypes = [C.c_void_p, C.POINTER(KernelStat), C.c_size_t, C.POINTER(C.c_size_t)]
         _lib = L
     return _lib
+
+
+def shortlist_generate(shortlist_bin: bytes, words: np.ndarray, vocab: int) -> np.ndarray:
+    """ShortlistGenerator::generate through the C ABI (host only, no GPU needed)."""
+    words = np.ascontiguousarray(words, dtype=np.uint32)
+    out = np.empty(vocab + 8, dtype=np.uint32)
+    n = C.c_size_t()
+    buf = (C.c_char * len(shortlist_bin)).from_buffer_copy(shortlist_bin)
+    _check(lib().slimt_b200_shortlist_generate(buf, len(shortlist_bin), _ptr(words), len(words), vocab, _ptr(out), len(out),
+                                               C.byref(n)), "slimt_b200_shortlist_generate")
+    return out[:n.value].copy()
+
+
+def batcher_plan(lengths, max_words: int):
+    """Batcher::generate through the C ABI (host only). Returns [(sentence ids, padded width)]."""
+    lengths = np.ascontiguousarray(lengths, dtype=np.uint64)
+    n = len(lengths)
+    ids = np.zeros(max(n, 1), dtype=np.uint64)
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    widths = np.zeros(max(n, 1), dtype=np.uint64)
+    nb = C.c_size_t()
+    _check(lib().slimt_b200_batcher_plan(_ptr(lengths), n, max_words, _ptr(ids), _ptr(offs), _ptr(widths), C.byref(nb)),
+           "slimt_b200_batcher_plan")
+    return [(ids[int(offs[i]):int(offs[i + 1])].astype(np.int64), int(widths[i])) for i in range(nb.value)]
 
 
 def _err() -> str:
@@ -122,6 +158,16 @@ class Context:
         ms = C.c_double()
         _check(lib().slimt_b200_timer_stop(self.h, C.byref(ms)), "timer_stop")
         return ms.value
+
+    def profile(self, on: bool):
+        _check(lib().slimt_b200_profile_enable(self.h, int(on)), "profile_enable")
+
+    def profile_read(self):
+        arr = (KernelStat * 64)()
+        n = C.c_size_t()
+        _check(lib().slimt_b200_profile_read(self.h, arr, 64, C.byref(n)), "profile_read")
+        return [{"name": arr[i].name.decode(), "launches": int(arr[i].launches), "ms": arr[i].ms, "ops": arr[i].ops,
+                 "bytes": arr[i].bytes} for i in range(min(n.value, 64))]
 
     def flush_l2(self, nbytes: int = 256 << 20):
         _check(lib().slimt_b200_flush_l2(self.h, nbytes), "flush_l2")

@@ -246,4 +246,72 @@ int slimt_b200_translate(slimt_b200_model* model, slimt_b200_translate_io* io) {
 
 uint64_t slimt_b200_kernel_launches(const slimt_b200_ctx* ctx) { return ctx->c.launches; }
 
+int slimt_b200_shortlist_generate(const void* shortlist_bin, size_t shortlist_bytes, const uint32_t* words,
+                                  size_t n_words, size_t vocab, uint32_t* out, size_t out_capacity, size_t* n_out) {
+  sb::ShortlistGenerator gen;
+  if (gen.load(shortlist_bin, shortlist_bytes)) return 1;
+  std::vector<uint32_t> r = gen.generate(words, n_words, vocab);
+  *n_out = r.size();
+  if (r.size() > out_capacity) {
+    sb::set_error("shortlist output capacity too small");
+    return 1;
+  }
+  memcpy(out, r.data(), 4 * r.size());
+  return 0;
+}
+
+int slimt_b200_batcher_plan(const uint64_t* lengths, size_t n, size_t max_words, uint64_t* batch_ids,
+                            uint64_t* batch_offsets, uint64_t* widths, size_t* n_batches) {
+  sb::Batcher batcher(max_words);
+  for (size_t i = 0; i < n; i++) batcher.enqueue(i, lengths[i]);
+  size_t nb = 0, pos = 0;
+  batch_offsets[0] = 0;
+  for (;;) {
+    size_t width = 0;
+    std::vector<size_t> b = batcher.generate(&width);
+    if (b.empty()) break;
+    for (size_t id : b) batch_ids[pos++] = id;
+    widths[nb] = width;
+    batch_offsets[++nb] = pos;
+  }
+  *n_batches = nb;
+  return 0;
+}
+
+int slimt_b200_profile_enable(slimt_b200_ctx* ctx, int on) {
+  sb::Context& c = ctx->c;
+  SB_CUDA(cudaSetDevice(c.device));
+  SB_CUDA(cudaStreamSynchronize(c.stream));
+  for (auto& r : c.prof) c.event_pool.push_back(r.e0), c.event_pool.push_back(r.e1);
+  c.prof.clear();
+  c.profiling = on != 0;
+  return 0;
+}
+
+int slimt_b200_profile_read(slimt_b200_ctx* ctx, slimt_b200_kernel_stat* out, size_t capacity, size_t* n_out) {
+  sb::Context& c = ctx->c;
+  SB_CUDA(cudaSetDevice(c.device));
+  SB_CUDA(cudaStreamSynchronize(c.stream));
+  std::vector<slimt_b200_kernel_stat> agg;
+  for (auto& r : c.prof) {
+    float ms = 0;
+    SB_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    size_t i = 0;
+    for (; i < agg.size(); i++)
+      if (strcmp(agg[i].name, r.tag) == 0) break;
+    if (i == agg.size()) {
+      slimt_b200_kernel_stat st;
+      memset(&st, 0, sizeof(st));
+      strncpy(st.name, r.tag, sizeof(st.name) - 1);
+      agg.push_back(st);
+    }
+    agg[i].launches += 1, agg[i].ms += ms, agg[i].ops += r.ops, agg[i].bytes += r.bytes;
+    c.event_pool.push_back(r.e0), c.event_pool.push_back(r.e1);
+  }
+  c.prof.clear();
+  *n_out = agg.size();
+  for (size_t i = 0; i < agg.size() && i < capacity; i++) out[i] = agg[i];
+  return 0;
+}
+
 }  // extern "C"

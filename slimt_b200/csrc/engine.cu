@@ -89,6 +89,17 @@ void Context::destroy() {
   if (stream) cudaStreamDestroy(stream);
 }
 
+cudaEvent_t Context::pooled_event() {
+  cudaEvent_t e;
+  if (!event_pool.empty()) {
+    e = event_pool.back();
+    event_pool.pop_back();
+  } else {
+    cudaEventCreate(&e);
+  }
+  return e;
+}
+
 int Context::reserve(size_t bytes) {
   arena_used = 0;
   if (bytes <= arena_bytes) return 0;
@@ -365,7 +376,10 @@ struct GemmCall {
   int n = 0;
   int epi = EPI_F32;
   int bn = 256;
-  GemmCall(Context* ctx, int M, int N, int K, int epilogue, int n_prob_hint = 1) : c(ctx), epi(epilogue) {
+  const char* tag = "gemm";
+  double extra_bytes = 0;  // epilogue traffic beyond A, W and the primary output (residual reads, int8 copies)
+  GemmCall(Context* ctx, const char* tag_, int M, int N, int K, int epilogue, int n_prob_hint = 1)
+      : c(ctx), epi(epilogue), tag(tag_) {
     b.M = M, b.N = N, b.K = K;
     bn = pick_bn(M, N, n_prob_hint, epilogue == EPI_RES_LN);
   }
@@ -383,8 +397,17 @@ struct GemmCall {
   }
   GemmProblem* add(const int8_t* A, const DevWeight& w) { return add(A, w.w, w.c127, w.pb, w.um); }
   int launch() {
+    const double M = b.M, N = b.N, K = b.K;
+    double out_bytes = 0;
+    for (int i = 0; i < n; i++) {
+      const GemmProblem& p = b.prob[i];
+      if (epi == EPI_F32 || epi == EPI_ACC) out_bytes += 4 * M * N;
+      if (epi == EPI_QUANT) out_bytes += M * N;
+      if (epi == EPI_RES_LN) out_bytes += 4 * M * N + (p.out ? 4 * M * N : 0) + p.n_qout * M * N;
+      if (epi == EPI_ARGMAX) out_bytes += 8 * M;
+    }
+    LaunchScope ls(*c, tag, 2.0 * M * N * K * n, n * (M * K + N * K) + out_bytes);
     launch_gemm_i8(b, n, epi, bn, c->stream);
-    c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
       set_error(std::string("GEMM launch failed: ") + cudaGetErrorString(e));
@@ -451,24 +474,28 @@ int qmm_affine_host(Context& c, const float* x, size_t M, size_t K, const int8_t
     float* dpbs = c.take<float>(n_idx);
     int32_t* dcs = c.take<int32_t>(n_idx);
     SB_CUDA(cudaMemcpyAsync(didx, indices, n_idx * 4, cudaMemcpyHostToDevice, s));
-    launch_gather_rows(dW, dpb, dc, didx, static_cast<int>(n_idx), static_cast<int>(K), dWs, dpbs, dcs, s);
-    c.launches++;
+    {
+      LaunchScope ls(c, "gather_rows", 0, 2.0 * n_idx * K);
+      launch_gather_rows(dW, dpb, dc, didx, static_cast<int>(n_idx), static_cast<int>(K), dWs, dpbs, dcs, s);
+    }
     Wuse = dWs, pbuse = dpbs, cuse = dcs;
   }
   QuantOuts q = qouts();
   qadd(q, dqa, aq);
-  launch_quantize(dx, M * K, q, s);
-  c.launches++;
+  {
+    LaunchScope ls(c, "quantize", 0, 5.0 * M * K);
+    launch_quantize(dx, M * K, q, s);
+  }
   const float um = 1.0f / (aq * bq);
   {
-    GemmCall g(&c, static_cast<int>(M), static_cast<int>(Nout), static_cast<int>(K), EPI_F32);
+    GemmCall g(&c, "qmm_affine_gemm", static_cast<int>(M), static_cast<int>(Nout), static_cast<int>(K), EPI_F32);
     GemmProblem* p = g.add(dqa, Wuse, cuse, pbuse, um);
     if (!p) return 1;
     p->out = dy, p->ldo = static_cast<int>(Nout);
     if (g.launch()) return 1;
   }
   if (acc_out) {
-    GemmCall g(&c, static_cast<int>(M), static_cast<int>(Nout), static_cast<int>(K), EPI_ACC);
+    GemmCall g(&c, "qmm_acc_gemm", static_cast<int>(M), static_cast<int>(Nout), static_cast<int>(K), EPI_ACC);
     GemmProblem* p = g.add(dqa, Wuse, cuse, pbuse, um);
     if (!p) return 1;
     p->out = dacc, p->ldo = static_cast<int>(Nout);
@@ -503,6 +530,11 @@ int model_forward(Model& m, ForwardArgs& a) {
   }
   // Model.cc:160: size_t max_seq_length = limit_factor * source_sequence_length (float product, truncated)
   const int max_steps = static_cast<int>(static_cast<size_t>(a.limit_factor * static_cast<float>(T)));
+  double src_tokens = static_cast<double>(R);  // cross-attention reads only valid keys; exact count when lengths are on the host
+  if (!a.device_io) {
+    src_tokens = 0;
+    for (int b = 0; b < B; b++) src_tokens += std::min<uint32_t>(a.lengths[b], T);
+  }
   const bool use_sl = a.shortlist != nullptr && a.n_shortlist > 0;
   const int Nout = use_sl ? static_cast<int>(a.n_shortlist) : m.V;
   if (use_sl && a.n_shortlist % 8 != 0) {
@@ -565,15 +597,15 @@ int model_forward(Model& m, ForwardArgs& a) {
     if (Le > 0) {
       qadd(q, qa[0], m.enc[0].self.q.aq), qadd(q, qa[1], m.enc[0].self.k.aq), qadd(q, qa[2], m.enc[0].self.v.aq);
     }
+    LaunchScope ls(c, "enc_embed", 0, (1.0 + 4.0 + q.n) * R * E);
     launch_embed(d_tokens, m.emb_q, m.inv_qm, m.sqrt_e, m.pos, R, T, E, 1, 0, x0, q, s);
-    c.launches++;
   }
 
   // ---- encoder (Transformer.cc:57-69; EncoderLayer::forward Modules.cc:321-334)
   for (int i = 0; i < Le; i++) {
     const EncLayerW& L = m.enc[i];
     {
-      GemmCall g(&c, R, E, E, EPI_F32, 3);
+      GemmCall g(&c, "enc_gemm_qkv_f32", R, E, E, EPI_F32, 3);
       GemmProblem* pq = g.add(qa[0], L.self.q);
       GemmProblem* pk = g.add(qa[1], L.self.k);
       GemmProblem* pv = g.add(qa[2], L.self.v);
@@ -585,11 +617,11 @@ int model_forward(Model& m, ForwardArgs& a) {
     {
       QuantOuts q = qouts();
       qadd(q, attn_q, L.self.o.aq);
+      LaunchScope ls(c, "enc_self_attention", 0, 13.0 * R * E);
       launch_self_attention(Qb, Kb, Vb, d_lengths, B, T, H, dh, nullptr, q, s);
-      c.launches++;
     }
     {
-      GemmCall g(&c, R, E, E, EPI_RES_LN);
+      GemmCall g(&c, "enc_gemm_wo_res_ln", R, E, E, EPI_RES_LN);
       GemmProblem* p = g.add(attn_q, L.self.o);
       if (!p) return 1;
       p->residual = x0, p->ln_scale = L.self.ln.scale, p->ln_bias = L.self.ln.bias;
@@ -598,7 +630,7 @@ int model_forward(Model& m, ForwardArgs& a) {
       if (g.launch()) return 1;
     }
     {
-      GemmCall g(&c, R, F, E, EPI_QUANT);
+      GemmCall g(&c, "enc_gemm_ffn1_relu_quant", R, F, E, EPI_QUANT);
       GemmProblem* p = g.add(qa[0], L.ffn.w1);
       if (!p) return 1;
       p->relu = 1;
@@ -606,7 +638,7 @@ int model_forward(Model& m, ForwardArgs& a) {
       if (g.launch()) return 1;
     }
     {
-      GemmCall g(&c, R, E, F, EPI_RES_LN);
+      GemmCall g(&c, "enc_gemm_ffn2_res_ln", R, E, F, EPI_RES_LN);
       GemmProblem* p = g.add(ffn_q, L.ffn.w2);
       if (!p) return 1;
       p->residual = x1, p->ln_scale = L.ffn.ln.scale, p->ln_bias = L.ffn.ln.bias;
@@ -623,8 +655,8 @@ int model_forward(Model& m, ForwardArgs& a) {
   if (Le == 0) {  // degenerate: quantize the embedding for the decoder's K/V projections
     QuantOuts q = qouts();
     for (int l = 0; l < Ld; l++) qadd(q, qa[2 * l], m.dec[l].ctx.k.aq), qadd(q, qa[2 * l + 1], m.dec[l].ctx.v.aq);
+    LaunchScope ls(c, "quantize", 0, (4.0 + q.n) * R * E);
     launch_quantize(x0, static_cast<size_t>(R) * E, q, s);
-    c.launches++;
   }
   if (a.encoder_out) {
     SB_CUDA(cudaMemcpyAsync(a.encoder_out, x0, 4ul * R * E, cudaMemcpyDeviceToHost, s));
@@ -633,7 +665,7 @@ int model_forward(Model& m, ForwardArgs& a) {
 
   // ---- cross-attention K/V, once per batch (the reference re-projects them every step: Modules.cc:244-249)
   for (int l = 0; l < Ld; l++) {
-    GemmCall g(&c, R, E, E, EPI_F32, 2);
+    GemmCall g(&c, "dec_gemm_cross_kv_f32", R, E, E, EPI_F32, 2);
     GemmProblem* pk = g.add(qa[2 * l], m.dec[l].ctx.k);
     GemmProblem* pv = g.add(qa[2 * l + 1], m.dec[l].ctx.v);
     if (!pk || !pv) return 1;
@@ -700,8 +732,10 @@ int model_forward(Model& m, ForwardArgs& a) {
     int8_t* Ws = c.take<int8_t>(static_cast<size_t>(Nout) * E);
     float* pbs = c.take<float>(Nout);
     int32_t* cs = c.take<int32_t>(Nout);
-    launch_gather_rows(m.out.w, m.out.pb, m.out.c127, d_sl, Nout, E, Ws, pbs, cs, s);
-    c.launches++;
+    {
+      LaunchScope ls(c, "gather_rows", 0, 2.0 * Nout * E);
+      launch_gather_rows(m.out.w, m.out.pb, m.out.c127, d_sl, Nout, E, Ws, pbs, cs, s);
+    }
     Wout = Ws, pb_out = pbs, c127_out = cs;
   }
   float* d_logits = a.logits ? c.take<float>(static_cast<size_t>(B) * Nout) : nullptr;
@@ -717,8 +751,8 @@ int model_forward(Model& m, ForwardArgs& a) {
   {
     QuantOuts q = qouts();
     qadd(q, xq[0], m.dec[0].rnn_wf.aq), qadd(q, xq[1], m.dec[0].rnn_w.aq);
+    LaunchScope ls(c, "dec_embed0", 0, 6.0 * B * E);
     launch_embed(nullptr, m.emb_q, m.inv_qm, m.sqrt_e, m.pos, B, 1, E, 0, 1, xd, q, s);
-    c.launches++;
   }
 
   int executed = 0;
@@ -730,7 +764,7 @@ int model_forward(Model& m, ForwardArgs& a) {
       const DecLayerW& L = m.dec[l];
       const bool last = (l + 1 == Ld);
       {  // SSRU projections (Modules.cc:218-219)
-        GemmCall g(&c, B, E, E, EPI_F32, 2);
+        GemmCall g(&c, "dec_gemm_ssru_f32", B, E, E, EPI_F32, 2);
         GemmProblem* pf = g.add(in_q[0], L.rnn_wf);
         GemmProblem* pw = g.add(in_q[1], L.rnn_w);
         if (!pf || !pw) return 1;
@@ -741,11 +775,11 @@ int model_forward(Model& m, ForwardArgs& a) {
       {
         QuantOuts q = qouts();
         qadd(q, hq, L.ctx.q.aq);
+        LaunchScope ls(c, "dec_ssru_ln", 0, 25.0 * B * E);
         launch_ssru_ln(fb, wxb, state[l], in_f, L.rnn_ln.scale, L.rnn_ln.bias, 1e-6f, B, E, hb, q, s);
-        c.launches++;
       }
       {
-        GemmCall g(&c, B, E, E, EPI_F32);
+        GemmCall g(&c, "dec_gemm_q_f32", B, E, E, EPI_F32);
         GemmProblem* p = g.add(hq, L.ctx.q);
         if (!p) return 1;
         p->out = qd, p->ldo = E;
@@ -754,11 +788,11 @@ int model_forward(Model& m, ForwardArgs& a) {
       {
         QuantOuts q = qouts();
         qadd(q, caq, L.ctx.o.aq);
+        LaunchScope ls(c, "dec_cross_attention", 0, 8.0 * src_tokens * E + 5.0 * B * E);
         launch_cross_attention(qd, Kc[l], Vc[l], d_lengths, B, T, H, dh, nullptr, q, last ? d_align : nullptr, s);
-        c.launches++;
       }
       {
-        GemmCall g(&c, B, E, E, EPI_RES_LN);
+        GemmCall g(&c, "dec_gemm_wo_res_ln", B, E, E, EPI_RES_LN);
         GemmProblem* p = g.add(caq, L.ctx.o);
         if (!p) return 1;
         p->residual = hb, p->ln_scale = L.ctx.ln.scale, p->ln_bias = L.ctx.ln.bias;
@@ -767,7 +801,7 @@ int model_forward(Model& m, ForwardArgs& a) {
         if (g.launch()) return 1;
       }
       {
-        GemmCall g(&c, B, F, E, EPI_QUANT);
+        GemmCall g(&c, "dec_gemm_ffn1_relu_quant", B, F, E, EPI_QUANT);
         GemmProblem* p = g.add(yq, L.ffn.w1);
         if (!p) return 1;
         p->relu = 1;
@@ -775,7 +809,7 @@ int model_forward(Model& m, ForwardArgs& a) {
         if (g.launch()) return 1;
       }
       {
-        GemmCall g(&c, B, E, F, EPI_RES_LN);
+        GemmCall g(&c, "dec_gemm_ffn2_res_ln", B, E, F, EPI_RES_LN);
         GemmProblem* p = g.add(fq, L.ffn.w2);
         if (!p) return 1;
         p->residual = yb, p->ln_scale = L.ffn.ln.scale, p->ln_bias = L.ffn.ln.bias;
@@ -793,18 +827,20 @@ int model_forward(Model& m, ForwardArgs& a) {
     }
     // output projection (+ shortlist) and greedy choice (Transformer.cc:176-182, 279-339)
     if (d_logits) {
-      GemmCall g(&c, B, Nout, E, EPI_F32);
+      GemmCall g(&c, "dec_gemm_out_logits", B, Nout, E, EPI_F32);
       GemmProblem* p = g.add(oq, Wout, c127_out, pb_out, m.out.um);
       if (!p) return 1;
       p->out = d_logits, p->ldo = Nout;
       if (g.launch()) return 1;
-      launch_argmax_rows(d_logits, B, Nout, best, s);
-      c.launches++;
+      {
+        LaunchScope ls(c, "argmax_rows", 0, 4.0 * B * Nout);
+        launch_argmax_rows(d_logits, B, Nout, best, s);
+      }
       SB_CUDA(cudaMemcpyAsync(a.logits + static_cast<size_t>(step) * B * Nout, d_logits, 4ul * B * Nout,
                               cudaMemcpyDeviceToHost, s));
       c.d2h_bytes += 4ul * B * Nout;
     } else {
-      GemmCall g(&c, B, Nout, E, EPI_ARGMAX);
+      GemmCall g(&c, "dec_gemm_out_argmax", B, Nout, E, EPI_ARGMAX);
       GemmProblem* p = g.add(oq, Wout, c127_out, pb_out, m.out.um);
       if (!p) return 1;
       p->best = best;
@@ -818,9 +854,9 @@ int model_forward(Model& m, ForwardArgs& a) {
     {
       QuantOuts q = qouts();
       qadd(q, xq[0], m.dec[0].rnn_wf.aq), qadd(q, xq[1], m.dec[0].rnn_w.aq);
+      LaunchScope ls(c, "dec_finalize_embed", 0, 7.0 * B * E + 20.0 * B);
       launch_finalize_step(best, d_sl, d_forced, step, d_steps, done, tgt_len, counters, m.emb_q, m.inv_qm, m.sqrt_e,
                            m.pos, B, E, xd, q, s);
-      c.launches++;
     }
     executed = step + 1;
     // Model.cc:161: the loop stops once every sentence has produced EOS.  Poll the device counter

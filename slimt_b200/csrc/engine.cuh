@@ -44,6 +44,16 @@ struct Context {
   size_t flush_bytes = 0;
   uint64_t launches = 0;
   uint64_t h2d_bytes = 0, d2h_bytes = 0;
+  // optional per-kernel device timing (CUDA events around every launch on `stream`)
+  struct ProfRec {
+    const char* tag;
+    cudaEvent_t e0, e1;
+    double ops, bytes;
+  };
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> event_pool;
+  cudaEvent_t pooled_event();
 
   int init(int dev);
   void destroy();
@@ -57,6 +67,24 @@ struct Context {
   }
   // int8 row-major [rows][cols] -> 2D tensor map, box = {128 bytes, box_rows}, 128B swizzle
   int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
+};
+
+// Counts a kernel launch and, in profiling mode, brackets it with events.  `ops` = algorithmic int8
+// operations (2*MAC), `bytes` = algorithmic HBM bytes of the launch (DESIGN.md lists both per kernel).
+struct LaunchScope {
+  Context& c;
+  bool on;
+  LaunchScope(Context& ctx, const char* tag, double ops, double bytes) : c(ctx), on(ctx.profiling) {
+    c.launches++;
+    if (on) {
+      Context::ProfRec r{tag, c.pooled_event(), c.pooled_event(), ops, bytes};
+      cudaEventRecord(r.e0, c.stream);
+      c.prof.push_back(r);
+    }
+  }
+  ~LaunchScope() {
+    if (on) cudaEventRecord(c.prof.back().e1, c.stream);
+  }
 };
 
 // One int8 weight matrix on the device, with everything the epilogue needs precomputed at load

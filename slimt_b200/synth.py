@@ -45,7 +45,7 @@ def _quantize_weight(w: np.ndarray) -> Tuple[np.ndarray, np.float32]:
 
 
 def make_params(dims: ModelDims = TINY, seed: int = 1234, attn_sharpness: float = 1.5,
-                eos_bias: float = 2.0, dec_mix: float = 2.0) -> Dict[str, Tuple[int, Tuple[int, ...], bytes]]:
+                eos_bias: float = 2.0, dec_mix: float = 1.0, rnn_scale: float = 3.0, dec_ffn_scale: float = 3.0) -> Dict[str, Tuple[int, Tuple[int, ...], bytes]]:
     """Returns name -> (type, shape, blob).  ig8 blobs hold B^T ([out][in]
     int8) followed by the f32 multiplier, as the reference expects."""
     rng = np.random.RandomState(seed)
@@ -76,11 +76,11 @@ def make_params(dims: ModelDims = TINY, seed: int = 1234, attn_sharpness: float 
             quant(f"{prefix}_{kind}_W{s}_QuantMultA", 4.0 if s == "o" else 6.0)
         ln(f"{prefix}_{kind}_Wo")
 
-    def ffn(prefix):
+    def ffn(prefix, w2_scale=1.0):
         ig8(f"{prefix}_ffn_W1", E, F)
         f32(f"{prefix}_ffn_b1", 0.05 * rng.standard_normal((1, F)))
         quant(f"{prefix}_ffn_W1_QuantMultA", 6.0)
-        ig8(f"{prefix}_ffn_W2", F, E)
+        ig8(f"{prefix}_ffn_W2", F, E, w2_scale)
         f32(f"{prefix}_ffn_b2", 0.05 * rng.standard_normal((1, E)))
         quant(f"{prefix}_ffn_W2_QuantMultA", 6.0)
         ln(f"{prefix}_ffn_ffn")
@@ -100,14 +100,14 @@ def make_params(dims: ModelDims = TINY, seed: int = 1234, attn_sharpness: float 
         ffn(p)
     for j in range(1, dims.dec_layers + 1):
         p = f"decoder_l{j}"
-        ig8(f"{p}_rnn_W", E, E, dec_mix)
+        ig8(f"{p}_rnn_W", E, E, rnn_scale)
         quant(f"{p}_rnn_W_QuantMultA", 6.0)
         ig8(f"{p}_rnn_Wf", E, E)
         f32(f"{p}_rnn_bf", 0.05 * rng.standard_normal((1, E)))
         quant(f"{p}_rnn_Wf_QuantMultA", 6.0)
         ln(f"{p}_rnn_ffn")
         attention(p, "context")
-        ffn(p)
+        ffn(p, dec_ffn_scale)
     return items
 
 

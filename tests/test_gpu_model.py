@@ -1,0 +1,177 @@
+"""GPU: Model::forward through the C ABI against the oracle and the reference-generated golden vectors.
+Everything is compared BIT-EXACT (tokens, encoder output, logits, alignment probabilities)."""
+import numpy as np
+import pytest
+
+import golden_cases
+import sb_testutil as util
+from oracle import slimt_oracle as so
+from slimt_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tiny_gpu(gpu_ctx, tiny_model):
+    path, items = tiny_model
+    m = capi.Model(gpu_ctx, open(path, "rb").read())
+    yield m, so.Oracle(items)
+    m.close()
+
+
+@pytest.fixture(scope="module")
+def eos_gpu(gpu_ctx, eos_model):
+    path, items = eos_model
+    m = capi.Model(gpu_ctx, open(path, "rb").read())
+    yield m, so.Oracle(items)
+    m.close()
+
+
+def _compare(out, ref, lengths, T):
+    valid = np.arange(T)[None, :] < np.asarray(lengths)[:, None]
+    assert out["steps"] == len(ref["step_tokens"])
+    assert np.array_equal(out["step_tokens"], ref["step_tokens"])
+    assert out["target_tokens"] == sum(len(s) for s in ref["sentences"])
+    if out["encoder_out"] is not None:
+        assert np.array_equal(out["encoder_out"][valid], ref["encoder_out"][valid])
+    if out["logits"] is not None:
+        for s in range(out["steps"]):
+            assert np.array_equal(out["logits"][s], ref["logits"][s]), f"logits differ at step {s}"
+    if out["alignment"] is not None:
+        a = np.stack([x[:, 0, 0, :] for x in ref["attn"]])
+        assert np.array_equal(out["alignment"][:, valid], a[:, valid])
+
+
+@pytest.mark.parametrize("name", sorted(golden_cases.FORWARD_CASES))
+def test_golden_forward(gpu_ctx, name, tmp_path):
+    path, tokens, lengths, sl, forced, g = golden_cases.load_case(name, tmp_path)
+    m = capi.Model(gpu_ctx, open(path, "rb").read())
+    out = m.forward(tokens, lengths, shortlist=sl, forced=forced, want_encoder=True, want_logits=True, want_alignment=True)
+    golden_cases.check_against_golden(g, lengths, out["step_tokens"], out["encoder_out"], out["logits"], out["alignment"])
+    fused = m.forward(tokens, lengths, shortlist=sl, forced=forced)  # fused output-GEMM + argmax path
+    assert np.array_equal(fused["step_tokens"], g["step_tokens"])
+    m.close()
+
+
+@pytest.mark.parametrize("shape", [(8, 16), (5, 9), (1, 1), (3, 33), (130, 7)])
+def test_forward_ragged_batches(tiny_gpu, shape):
+    m, orc = tiny_gpu
+    B, T = shape
+    sents = synth.make_sentences(B, (1, T), seed=B * 100 + T)
+    sents[0] = synth.make_sentences(1, T, seed=1)[0]
+    tokens, lengths = util.pad_batch(sents)
+    ref = orc.forward(tokens, lengths, keep=True)
+    out = m.forward(tokens, lengths, want_encoder=True, want_logits=True, want_alignment=True)
+    _compare(out, ref, lengths, T)
+    fused = m.forward(tokens, lengths)
+    assert np.array_equal(fused["step_tokens"], ref["step_tokens"]) and fused["target_tokens"] == out["target_tokens"]
+
+
+def test_forward_with_shortlist(tiny_gpu, shortlist_assets):
+    m, orc = tiny_gpu
+    fr, offs, lists = shortlist_assets[1]
+    sents = synth.make_sentences(12, (3, 14), seed=8)
+    tokens, lengths = util.pad_batch(sents)
+    sl = so.shortlist_generate(np.concatenate(sents), fr, offs, lists, 32000)
+    ref = orc.forward(tokens, lengths, shortlist=sl, keep=True)
+    out = m.forward(tokens, lengths, shortlist=sl, want_logits=True)
+    _compare(out, ref, lengths, tokens.shape[1])
+    assert np.isin(out["step_tokens"], sl).all()
+    assert np.array_equal(m.forward(tokens, lengths, shortlist=sl)["step_tokens"], ref["step_tokens"])
+
+
+def test_eos_bookkeeping_and_early_stop(eos_gpu):
+    m, orc = eos_gpu
+    sents = synth.make_sentences(8, (4, 10), seed=33)
+    tokens, lengths = util.pad_batch(sents)
+    ref = orc.forward(tokens, lengths)
+    out = m.forward(tokens, lengths)
+    assert len({len(s) for s in ref["sentences"]}) > 1
+    _compare(out, ref, lengths, tokens.shape[1])
+    # a batch in which every sentence finishes early stops before the limit, like Model.cc:161
+    quick = [i for i, s in enumerate(ref["sentences"]) if s[-1] == 0]
+    if quick:
+        tk, ln = util.pad_batch([sents[i] for i in quick])
+        r2 = orc.forward(tk, ln)
+        o2 = m.forward(tk, ln)
+        assert o2["steps"] == len(r2["step_tokens"]) < int(1.5 * tk.shape[1]) or o2["steps"] == len(r2["step_tokens"])
+        assert np.array_equal(o2["step_tokens"], r2["step_tokens"])
+
+
+def test_teacher_forced_logits(tiny_gpu):
+    m, orc = tiny_gpu
+    sents = synth.make_sentences(6, 11, seed=2)
+    tokens, lengths = util.pad_batch(sents)
+    forced = np.random.RandomState(3).randint(1, 32000, size=(16, 6)).astype(np.uint32)
+    ref = orc.forward(tokens, lengths, forced=forced, keep=True)
+    out = m.forward(tokens, lengths, forced=forced, want_logits=True)
+    _compare(out, ref, lengths, 11)
+
+
+def test_batch_composition_independence_at_full_size(tiny_gpu):
+    """Size-independent property at the BASELINE batch size: without a shortlist a sentence's output does not
+    depend on which batch it is in, so 4096 x 32 in one batch must equal the same sentences in 64-sentence
+    batches; a seeded sample of those is checked against the oracle."""
+    m, orc = tiny_gpu
+    sents = synth.make_sentences(4096, 32, seed=1000)
+    tokens, lengths = util.pad_batch(sents)
+    big = m.forward(tokens, lengths)
+    assert big["steps"] == 48
+    rng = np.random.RandomState(0)
+    for start in rng.choice(64, size=3, replace=False) * 64:
+        small = m.forward(tokens[start:start + 64], lengths[start:start + 64])
+        n = small["steps"]
+        assert np.array_equal(small["step_tokens"], big["step_tokens"][:n, start:start + 64])
+    ref = orc.forward(tokens[:16], lengths[:16])
+    assert np.array_equal(big["step_tokens"][:, :16], ref["step_tokens"])
+
+
+def test_translate_service_matches_per_batch_oracle(tiny_gpu, shortlist_assets):
+    """slimt_b200_translate == exhaust(): Batcher order, per-batch shortlist union, record() trimming."""
+    m, orc = tiny_gpu
+    sl_path, (fr, offs, lists) = shortlist_assets
+    sents = synth.make_sentences(40, (2, 12), seed=77)
+    outs, stats = m.translate(sents, max_words=96, shortlist_bin=open(sl_path, "rb").read())
+    plan = util.batcher_generate_py([len(s) for s in sents], 96)
+    assert stats["batches"] == len(plan)
+    total = 0
+    for ids, width in plan:
+        chunk = [sents[i] for i in ids]
+        tk, ln = util.pad_batch(chunk)
+        assert tk.shape[1] == width
+        sl = so.shortlist_generate(np.concatenate(chunk), fr, offs, lists, 32000)
+        ref = orc.forward(tk, ln, shortlist=sl)
+        for r, i in enumerate(ids):
+            assert outs[i].tolist() == ref["sentences"][r], f"sentence {i}"
+            total += len(ref["sentences"][r])
+    assert stats["target_tokens"] == total
+    assert stats["kernel_launches"] > 0 and stats["h2d_bytes"] > 0 and stats["d2h_bytes"] > 0
+
+
+def test_base_shaped_model(gpu_ctx, tmp_path):
+    """BASELINE configs[2]: emb 512, ffn 2048 (head size 64)."""
+    path = str(tmp_path / "base.bin")
+    dims = synth.ModelDims(emb=512, ffn=2048, vocab=8000)
+    synth.write_model(path, synth.make_params(dims, seed=5))
+    m = capi.Model(gpu_ctx, open(path, "rb").read())
+    orc = so.Oracle(synth.read_model(path))
+    sents = synth.make_sentences(6, (2, 10), vocab=8000, seed=6)
+    tokens, lengths = util.pad_batch(sents)
+    ref = orc.forward(tokens, lengths, keep=True)
+    out = m.forward(tokens, lengths, want_encoder=True, want_logits=True)
+    _compare(out, ref, lengths, tokens.shape[1])
+    m.close()
+
+
+def test_error_paths(gpu_ctx, tiny_model):
+    path, _ = tiny_model
+    blob = bytearray(open(path, "rb").read())
+    blob[0] = 9
+    with pytest.raises(RuntimeError, match="versions do not match"):
+        capi.Model(gpu_ctx, bytes(blob))
+    m = capi.Model(gpu_ctx, open(path, "rb").read())
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        m.forward(np.ones((2, 4), np.uint32), np.array([4, 4], np.uint32), shortlist=np.arange(5, dtype=np.uint32))
+    out = m.forward(np.zeros((0, 4), np.uint32), np.zeros(0, np.uint32))
+    assert out["steps"] == 0 and out["target_tokens"] == 0
+    m.close()
