@@ -66,6 +66,7 @@ int Context::init(int dev) {
               std::to_string(prop.minor));
     return 1;
   }
+  num_sms = prop.multiProcessorCount;
   SB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   SB_CUDA(cudaEventCreate(&ev0));
   SB_CUDA(cudaEventCreate(&ev1));
@@ -124,6 +125,21 @@ int Context::make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)) + " (rows=" +
               std::to_string(rows) + ", cols=" + std::to_string(cols) + ")");
+    return 1;
+  }
+  return 0;
+}
+
+int Context::make_map_f32(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 4};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (f32) failed with CUresult " + std::to_string(static_cast<int>(r)));
     return 1;
   }
   return 0;
@@ -586,9 +602,12 @@ int model_forward(Model& m, ForwardArgs& a) {
   int8_t* attn_q = c.take<int8_t>(static_cast<size_t>(R) * E);
   int8_t* ffn_q = c.take<int8_t>(static_cast<size_t>(R) * F);
   std::vector<float*> Kc(Ld), Vc(Ld);
+  std::vector<CUtensorMap> mapKc(Ld), mapVc(Ld);
   for (int l = 0; l < Ld; l++) {
     Kc[l] = c.take<float>(static_cast<size_t>(R) * E);
     Vc[l] = c.take<float>(static_cast<size_t>(R) * E);
+    const uint32_t box_rows = static_cast<uint32_t>(cross_attention_box_rows(T));
+    if (c.make_map_f32(&mapKc[l], Kc[l], R, E, box_rows) || c.make_map_f32(&mapVc[l], Vc[l], R, E, box_rows)) return 1;
   }
 
   // ---- embedding (Model.cc:195-197)
@@ -789,7 +808,8 @@ int model_forward(Model& m, ForwardArgs& a) {
         QuantOuts q = qouts();
         qadd(q, caq, L.ctx.o.aq);
         LaunchScope ls(c, "dec_cross_attention", 0, 8.0 * src_tokens * E + 5.0 * B * E);
-        launch_cross_attention(qd, Kc[l], Vc[l], d_lengths, B, T, H, dh, nullptr, q, last ? d_align : nullptr, s);
+        launch_cross_attention(mapKc[l], mapVc[l], qd, d_lengths, B, T, H, dh, c.num_sms, nullptr, q,
+                               last ? d_align : nullptr, s);
       }
       {
         GemmCall g(&c, "dec_gemm_wo_res_ln", B, E, E, EPI_RES_LN);

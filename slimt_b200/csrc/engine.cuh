@@ -30,6 +30,7 @@ const char* last_error();
 
 struct Context {
   int device = 0;
+  int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // cuTensorMapEncodeTiled, fetched through the runtime so libcuda is not a link-time dependency
@@ -67,6 +68,8 @@ struct Context {
   }
   // int8 row-major [rows][cols] -> 2D tensor map, box = {128 bytes, box_rows}, 128B swizzle
   int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
+  // f32 row-major [rows][cols] -> 2D tensor map, box = {32 floats (128 bytes), box_rows}, 128B swizzle
+  int make_map_f32(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
 };
 
 // Counts a kernel launch and, in profiling mode, brackets it with events.  `ops` = algorithmic int8

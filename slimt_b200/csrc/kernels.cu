@@ -132,99 +132,6 @@ __global__ void self_attention_kernel(const float* __restrict__ Q, const float* 
   }
 }
 
-// ------------------------------------------------------------------ cross attention (decode)
-// Warp = one (sentence, head), one query.  Lane j scores key j (+32, +64 ...), the sum runs in key
-// order through shuffles, lane d accumulates output dim d over keys in order (coalesced V reads).
-constexpr int kMaxKeyRegs = 8;  // S <= 256
-
-template <int DH>
-__global__ void cross_attention_kernel(const float* __restrict__ Qr, const float* __restrict__ Kc,
-                                       const float* __restrict__ Vc, const uint32_t* __restrict__ lengths, int B,
-                                       int S, int H, float dk, float* __restrict__ out_f32, QuantOuts q,
-                                       float* __restrict__ attn_head0) {
-  extern __shared__ float smem_f[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  const int gw = blockIdx.x * wpb + warp;
-  if (gw >= B * H) return;
-  const int b = gw / H, h = gw % H;
-  const int E = H * DH;
-  const int len = min(static_cast<int>(lengths[b]), S);
-  float* sq = smem_f + warp * DH;
-  const float* qrow = Qr + static_cast<size_t>(b) * E + h * DH;
-  for (int d = lane; d < DH; d += 32) sq[d] = qrow[d];
-  __syncwarp();
-
-  const size_t kv_base = static_cast<size_t>(b) * S * E + static_cast<size_t>(h) * DH;
-  float sc[kMaxKeyRegs];
-  float mx = -3.402823466e+38f;
-#pragma unroll
-  for (int m = 0; m < kMaxKeyRegs; m++) {
-    const int j = m * 32 + lane;
-    sc[m] = 0.0f;
-    if (j < len) {
-      const float* kr = Kc + kv_base + static_cast<size_t>(j) * E;
-      float s = 0.0f;
-#pragma unroll
-      for (int d = 0; d < DH; d += 4) {
-        const float4 kk = *reinterpret_cast<const float4*>(kr + d);
-        s = fmaf(sq[d], kk.x, s);
-        s = fmaf(sq[d + 1], kk.y, s);
-        s = fmaf(sq[d + 2], kk.z, s);
-        s = fmaf(sq[d + 3], kk.w, s);
-      }
-      s = __fmul_rn(dk, s);
-      sc[m] = s;
-      mx = fmaxf(mx, s);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-#pragma unroll
-  for (int m = 0; m < kMaxKeyRegs; m++) {
-    const int j = m * 32 + lane;
-    sc[m] = (j < len) ? expf_glibc(__fsub_rn(sc[m], mx)) : 0.0f;
-  }
-  float sum = 0.0f;
-#pragma unroll
-  for (int m = 0; m < kMaxKeyRegs; m++) {
-    if (m * 32 < len) {
-      const int lim = min(32, len - m * 32);
-      for (int l = 0; l < lim; l++) sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, sc[m], l));
-    }
-  }
-#pragma unroll
-  for (int m = 0; m < kMaxKeyRegs; m++) sc[m] = __fdiv_rn(sc[m], sum);
-  if (attn_head0 != nullptr && h == 0) {
-#pragma unroll
-    for (int m = 0; m < kMaxKeyRegs; m++) {
-      const int j = m * 32 + lane;
-      if (j < S) attn_head0[static_cast<size_t>(b) * S + j] = (j < len) ? sc[m] : 0.0f;
-    }
-  }
-  float acc[DH / 32];
-#pragma unroll
-  for (int u = 0; u < DH / 32; u++) acc[u] = 0.0f;
-#pragma unroll
-  for (int m = 0; m < kMaxKeyRegs; m++) {
-    if (m * 32 < len) {
-      const int lim = min(32, len - m * 32);
-      for (int l = 0; l < lim; l++) {
-        const float p = __shfl_sync(0xffffffffu, sc[m], l);
-        const float* vr = Vc + kv_base + static_cast<size_t>(m * 32 + l) * E;
-#pragma unroll
-        for (int u = 0; u < DH / 32; u++) acc[u] = fmaf(p, vr[u * 32 + lane], acc[u]);
-      }
-    }
-  }
-  const size_t off = static_cast<size_t>(b) * E + h * DH;
-#pragma unroll
-  for (int u = 0; u < DH / 32; u++) {
-    if (out_f32) out_f32[off + u * 32 + lane] = acc[u];
-    for (int k = 0; k < q.n; k++) q.ptr[k][off + u * 32 + lane] = static_cast<int8_t>(quantize1(acc[u], q.aq[k]));
-  }
-}
-
 // ------------------------------------------------------------------ SSRU tail
 // Warp = one sentence row.  Elementwise part is lane-parallel and coalesced; the two LayerNorm sums
 // run in element order over the row parked in shared memory (every lane walks the same chain).
@@ -373,27 +280,6 @@ void launch_self_attention(const float* Q, const float* K, const float* V, const
   } else if (dh == 64) {
     cudaFuncSetAttribute(self_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     self_attention_kernel<64><<<B * H, threads, smem, stream>>>(Q, K, V, lengths, T, H, dk, out_f32, q);
-  } else {
-    fprintf(stderr, "slimt_b200: unsupported head dim %d\n", dh);
-    abort();
-  }
-}
-
-void launch_cross_attention(const float* Qr, const float* Kc, const float* Vc, const uint32_t* lengths, int B, int S,
-                            int H, int dh, float* out_f32, QuantOuts q, float* attn_head0, cudaStream_t stream) {
-  if (B == 0) return;
-  if (S > 32 * kMaxKeyRegs) {
-    fprintf(stderr, "slimt_b200: source length %d exceeds %d\n", S, 32 * kMaxKeyRegs);
-    abort();
-  }
-  const float dk = static_cast<float>(1.0 / std::sqrt(static_cast<double>(dh)));
-  const int wpb = 8;
-  const int blocks = (B * H + wpb - 1) / wpb;
-  const size_t smem = static_cast<size_t>(wpb) * dh * sizeof(float);
-  if (dh == 32) {
-    cross_attention_kernel<32><<<blocks, wpb * 32, smem, stream>>>(Qr, Kc, Vc, lengths, B, S, H, dk, out_f32, q, attn_head0);
-  } else if (dh == 64) {
-    cross_attention_kernel<64><<<blocks, wpb * 32, smem, stream>>>(Qr, Kc, Vc, lengths, B, S, H, dk, out_f32, q, attn_head0);
   } else {
     fprintf(stderr, "slimt_b200: unsupported head dim %d\n", dh);
     abort();

@@ -2,6 +2,7 @@
 // Each one reproduces the reference's f32 arithmetic bit for bit (see
 // exact_math.cuh) while emitting the int8 operands of the GEMMs that consume it.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -29,11 +30,13 @@ void launch_quantize(const float* x, size_t n, QuantOuts q, cudaStream_t stream)
 void launch_self_attention(const float* Q, const float* K, const float* V, const uint32_t* lengths, int B, int T,
                            int H, int dh, float* out_f32, QuantOuts q, cudaStream_t stream);
 
-// Decoder cross-attention for one query row per sentence over cached K,V [B][S][E].
+// Decoder cross-attention for one query row per sentence over cached K,V [B][S][E] (cross_attention.cu).
+// mapK/mapV: f32 tensor maps over [B*S][E] with box {32 floats, cross_attention_box_rows(S)}, 128B swizzle.
 // attn_head0 (optional) receives head 0's probabilities [B][S] (alignment, slimt/Model.cc:84-108).
-void launch_cross_attention(const float* Qr, const float* Kc, const float* Vc, const uint32_t* lengths, int B,
-                            int S, int H, int dh, float* out_f32, QuantOuts q, float* attn_head0,
-                            cudaStream_t stream);
+int cross_attention_box_rows(int S);
+void launch_cross_attention(const CUtensorMap& mapK, const CUtensorMap& mapV, const float* Qr,
+                            const uint32_t* lengths, int B, int S, int H, int dh, int num_sms, float* out_f32,
+                            QuantOuts q, float* attn_head0, cudaStream_t stream);
 
 // SSRU cell tail (slimt/Modules.cc:190-235): c = highway(c_prev, Wx, f); h = LN(x + relu(c)); state <- c.
 void launch_ssru_ln(const float* f, const float* wx, float* state, const float* x, const float* ln_scale,
