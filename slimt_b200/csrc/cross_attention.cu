@@ -18,9 +18,35 @@ namespace sb {
 
 namespace {
 
-constexpr int kMaxKeyRegs = 8;  // S <= 256
+constexpr int kMaxKeyChunks = 8;  // S <= 256
 
-template <int DH, int H>
+// glibc expf with its 32-entry table staged in shared memory (exact_math.cuh: expf_glibc reads it from global)
+__device__ __forceinline__ float expf_glibc_tab(float x, const uint64_t* tab) {
+  const double kInvLn2N = 0x1.71547652b82fep+0 * 32;
+  const double kShift = 0x1.8p+52;
+  const double kC0 = 0x1.c6af84b912394p-5 / 32 / 32 / 32;
+  const double kC1 = 0x1.ebfce50fac4f3p-3 / 32 / 32;
+  const double kC2 = 0x1.62e42ff0c52d6p-1 / 32;
+  if (x != x) return x + x;
+  if (x > 0x1.62e42ep6f) return __int_as_float(0x7f800000);
+  if (x < -0x1.9fe368p6f) return 0.0f;
+  double xd = (double)x;
+  double kd = fma(kInvLn2N, xd, kShift);
+  uint64_t ki = (uint64_t)__double_as_longlong(kd);
+  kd = __dsub_rn(kd, kShift);
+  double r = fma(kInvLn2N, xd, -kd);
+  uint64_t t = tab[ki & 31] + (ki << 47);
+  double s = __longlong_as_double((long long)t);
+  double z = fma(kC0, r, kC1);
+  double r2 = __dmul_rn(r, r);
+  double y = fma(kC2, r, 1.0);
+  y = fma(z, r2, y);
+  y = __dmul_rn(y, s);
+  return __double2float_rn(y);
+}
+
+// NC = compile-time bound on 32-key chunks per sentence (ceil(S / 32) rounded up to 1, 2, 4 or 8)
+template <int DH, int H, int NC>
 __global__ void __launch_bounds__((H + 1) * 32, 3)
     cross_attention_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV,
                            const float* __restrict__ Qr, const uint32_t* __restrict__ lengths, int B, int S,
@@ -34,9 +60,11 @@ __global__ void __launch_bounds__((H + 1) * 32, 3)
   const uint32_t chunk_bytes = tile_bytes * H * kSub;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * chunk_bytes);
   uint64_t* empty_bar = full_bar + stages;
-  float* sq_all = reinterpret_cast<float*>(empty_bar + stages);
+  uint64_t* exp_tab = empty_bar + stages;
+  float* sq_all = reinterpret_cast<float*>(exp_tab + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x >= 32 && threadIdx.x < 64) exp_tab[threadIdx.x - 32] = kExp2fTab[threadIdx.x - 32];
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapK);
     tma_prefetch_desc(&mapV);
@@ -91,10 +119,10 @@ __global__ void __launch_bounds__((H + 1) * 32, 3)
     __syncwarp();
     for (int d = lane; d < DH; d += 32) sq[d] = Qr[static_cast<size_t>(b) * E + h * DH + d];
     __syncwarp();
-    float sc[kMaxKeyRegs];
+    float sc[NC];
     float mx = -3.402823466e+38f;
 #pragma unroll
-    for (int c = 0; c < kMaxKeyRegs; c++) {
+    for (int c = 0; c < NC; c++) {
       sc[c] = 0.0f;
       if (c < nc) {
         const uint32_t s = it % stages;
@@ -128,10 +156,10 @@ __global__ void __launch_bounds__((H + 1) * 32, 3)
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float sum = 0.0f;
 #pragma unroll
-    for (int c = 0; c < kMaxKeyRegs; c++) {
+    for (int c = 0; c < NC; c++) {
       if (c < nc) {
         const int j = c * 32 + lane;
-        sc[c] = (j < len) ? expf_glibc(__fsub_rn(sc[c], mx)) : 0.0f;
+        sc[c] = (j < len) ? expf_glibc_tab(__fsub_rn(sc[c], mx), exp_tab) : 0.0f;
         // sum in key order (slimt/TensorOps.cc:296-314): exp of a masked key is +0 and adding it is exact
         __syncwarp();
         sp[lane] = sc[c];
@@ -147,12 +175,12 @@ __global__ void __launch_bounds__((H + 1) * 32, 3)
       }
     }
 #pragma unroll
-    for (int c = 0; c < kMaxKeyRegs; c++) {
+    for (int c = 0; c < NC; c++) {
       if (c < nc) sc[c] = __fdiv_rn(sc[c], sum);
     }
     if (attn_head0 != nullptr && h == 0) {
 #pragma unroll
-      for (int c = 0; c < kMaxKeyRegs; c++) {
+      for (int c = 0; c < NC; c++) {
         const int j = c * 32 + lane;
         if (j < S) attn_head0[static_cast<size_t>(b) * S + j] = (j < len) ? sc[c] : 0.0f;
       }
@@ -162,7 +190,7 @@ __global__ void __launch_bounds__((H + 1) * 32, 3)
 #pragma unroll
     for (int u = 0; u < kSub; u++) acc[u] = 0.0f;
 #pragma unroll
-    for (int c = 0; c < kMaxKeyRegs; c++) {
+    for (int c = 0; c < NC; c++) {
       if (c < nc) {
         const uint32_t s = it % stages;
         const uint32_t ph = (it / stages) & 1;
@@ -217,9 +245,9 @@ void launch_cross_attention(const CUtensorMap& mapK, const CUtensorMap& mapV, co
                             int B, int S, int H, int dh, int num_sms, float* out_f32, QuantOuts q, float* attn_head0,
                             cudaStream_t stream) {
   if (B == 0) return;
-  if (S > 32 * kMaxKeyRegs || H != 8 || (dh != 32 && dh != 64)) {
+  if (S > 32 * kMaxKeyChunks || H != 8 || (dh != 32 && dh != 64)) {
     fprintf(stderr, "slimt_b200: cross attention supports S <= %d, 8 heads of 32 or 64 (got S=%d H=%d dh=%d)\n",
-            32 * kMaxKeyRegs, S, H, dh);
+            32 * kMaxKeyChunks, S, H, dh);
     abort();
   }
   const float dk = static_cast<float>(1.0 / std::sqrt(static_cast<double>(dh)));
@@ -230,21 +258,32 @@ void launch_cross_attention(const CUtensorMap& mapK, const CUtensorMap& mapV, co
   // flight come from co-resident CTAs.
   int stages = 2;
   if (chunk <= 8 * 1024) stages = 4;
-  const size_t smem = 1024 + stages * chunk + stages * 16 + static_cast<size_t>(H) * (dh + 32) * sizeof(float);
+  const size_t smem = 1024 + stages * chunk + stages * 16 + 256 + static_cast<size_t>(H) * (dh + 32) * sizeof(float);
   int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 3) per_sm = 3;
   const int grid = B < num_sms * per_sm ? B : num_sms * per_sm;
   const int threads = (H + 1) * 32;
+  const int nc = (S + 31) / 32;
+#define SB_CA_LAUNCH(DH_, NC_)                                                                                   \
+  do {                                                                                                           \
+    auto kern = cross_attention_kernel<DH_, 8, NC_>;                                                             \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));             \
+    kern<<<grid, threads, smem, stream>>>(mapK, mapV, Qr, lengths, B, S, box_rows, stages, dk, out_f32, q,      \
+                                          attn_head0);                                                           \
+  } while (0)
   if (dh == 32) {
-    auto kern = cross_attention_kernel<32, 8>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    kern<<<grid, threads, smem, stream>>>(mapK, mapV, Qr, lengths, B, S, box_rows, stages, dk, out_f32, q, attn_head0);
+    if (nc <= 1) SB_CA_LAUNCH(32, 1);
+    else if (nc <= 2) SB_CA_LAUNCH(32, 2);
+    else if (nc <= 4) SB_CA_LAUNCH(32, 4);
+    else SB_CA_LAUNCH(32, 8);
   } else {
-    auto kern = cross_attention_kernel<64, 8>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    kern<<<grid, threads, smem, stream>>>(mapK, mapV, Qr, lengths, B, S, box_rows, stages, dk, out_f32, q, attn_head0);
+    if (nc <= 1) SB_CA_LAUNCH(64, 1);
+    else if (nc <= 2) SB_CA_LAUNCH(64, 2);
+    else if (nc <= 4) SB_CA_LAUNCH(64, 4);
+    else SB_CA_LAUNCH(64, 8);
   }
+#undef SB_CA_LAUNCH
 }
 
 }  // namespace sb

@@ -32,9 +32,8 @@ void host_quantize(const float* x, int8_t* q, float mult, size_t n) {
 }
 
 // Int8Shift::PrepareBias with UnquantizeAndAddBiasAndWrite (qmm/Intgemm.inl.cc:112-128):
-// pb[n] = float(colsum[n]) * ((-1*((127/aq)*(127/bq)))/127) + bias[n]; c127[n] = 127*colsum[n].
-void host_prepare_bias(const int8_t* Bt, const float* bias, float aq, float bq, size_t K, size_t N, float* pb,
-                       int32_t* c127) {
+// pb[n] = float(colsum[n]) * ((-1*((127/aq)*(127/bq)))/127) + bias[n].
+void host_prepare_bias(const int8_t* Bt, const float* bias, float aq, float bq, size_t K, size_t N, float* pb) {
   const float a_alpha = 127.0f / aq;
   const float b_alpha = 127.0f / bq;
   const float m = (-1.0f * (a_alpha * b_alpha)) / 127.0f;
@@ -44,7 +43,6 @@ void host_prepare_bias(const int8_t* Bt, const float* bias, float aq, float bq, 
     for (size_t k = 0; k < K; k++) cs += row[k];
     volatile float prod = static_cast<float>(cs) * m;  // keep mul and add separate (no contraction)
     pb[n] = prod + (bias ? bias[n] : 0.0f);
-    c127[n] = 127 * cs;
   }
 }
 
@@ -287,11 +285,9 @@ int Model::load(Context* c, const void* bin, size_t bytes, int enc_layers, int d
       return 1;
     }
     std::vector<float> pb(N);
-    std::vector<int32_t> c127(N);
-    host_prepare_bias(q, bias, w.aq, w.bq, K, N, pb.data(), c127.data());
+    host_prepare_bias(q, bias, w.aq, w.bq, K, N, pb.data());
     if (upload(q, static_cast<size_t>(K) * N, reinterpret_cast<void**>(&w.w))) return 1;
     if (upload(pb.data(), 4ul * N, reinterpret_cast<void**>(&w.pb))) return 1;
-    if (upload(c127.data(), 4ul * N, reinterpret_cast<void**>(&w.c127))) return 1;
     return 0;
   };
   auto ln = [&](const std::string& prefix, DevLN& l) -> int {
@@ -400,18 +396,18 @@ struct GemmCall {
     bn = pick_bn(M, N, n_prob_hint, epilogue == EPI_RES_LN);
   }
   // adds one problem; returns its slot (or nullptr on failure)
-  GemmProblem* add(const int8_t* A, const int8_t* Wt, const int32_t* c127, const float* pb, float um) {
+  GemmProblem* add(const int8_t* A, const int8_t* Wt, const float* pb, float um) {
     GemmProblem& p = b.prob[n];
     memset(&p, 0, sizeof(p));
     const uint32_t box_b = static_cast<uint32_t>(std::min(bn, 256));
     if (c->make_map(&p.tma_a, A, b.M, b.K, kBM)) return nullptr;
     if (c->make_map(&p.tma_b, Wt, b.N, b.K, box_b)) return nullptr;
-    p.c127 = c127, p.pb = pb, p.um = um;
+    p.pb = pb, p.um = um;
     p.ln_eps = 1e-6f;  // TensorOps.hh:67-68
     n++;
     return &p;
   }
-  GemmProblem* add(const int8_t* A, const DevWeight& w) { return add(A, w.w, w.c127, w.pb, w.um); }
+  GemmProblem* add(const int8_t* A, const DevWeight& w) { return add(A, w.w, w.pb, w.um); }
   int launch() {
     const double M = b.M, N = b.N, K = b.K;
     double out_bytes = 0;
@@ -463,8 +459,7 @@ int qmm_affine_host(Context& c, const float* x, size_t M, size_t K, const int8_t
   if (M == 0) return 0;
   // PrepareBias on the FULL B, then gather (qmm/Intgemm.inl.cc:33-66)
   std::vector<float> pb(N);
-  std::vector<int32_t> c127(N);
-  host_prepare_bias(W, bias, aq, bq, K, N, pb.data(), c127.data());
+  host_prepare_bias(W, bias, aq, bq, K, N, pb.data());
   const size_t Nout = indices ? n_idx : N;
   const size_t need = M * K * 5 + N * K + N * 8 + Nout * K + Nout * 8 + n_idx * 4 + M * Nout * 8 + 16 * 256;
   if (c.reserve(need)) return 1;
@@ -472,29 +467,25 @@ int qmm_affine_host(Context& c, const float* x, size_t M, size_t K, const int8_t
   int8_t* dqa = c.take<int8_t>(M * K);
   int8_t* dW = c.take<int8_t>(N * K);
   float* dpb = c.take<float>(N);
-  int32_t* dc = c.take<int32_t>(N);
   float* dy = c.take<float>(M * Nout);
   int32_t* dacc = c.take<int32_t>(M * Nout);
   cudaStream_t s = c.stream;
   SB_CUDA(cudaMemcpyAsync(dx, x, M * K * 4, cudaMemcpyHostToDevice, s));
   SB_CUDA(cudaMemcpyAsync(dW, W, N * K, cudaMemcpyHostToDevice, s));
   SB_CUDA(cudaMemcpyAsync(dpb, pb.data(), N * 4, cudaMemcpyHostToDevice, s));
-  SB_CUDA(cudaMemcpyAsync(dc, c127.data(), N * 4, cudaMemcpyHostToDevice, s));
   c.h2d_bytes += M * K * 4 + N * K + N * 8;
   const int8_t* Wuse = dW;
   const float* pbuse = dpb;
-  const int32_t* cuse = dc;
   if (indices) {
     uint32_t* didx = c.take<uint32_t>(n_idx);
     int8_t* dWs = c.take<int8_t>(n_idx * K);
     float* dpbs = c.take<float>(n_idx);
-    int32_t* dcs = c.take<int32_t>(n_idx);
     SB_CUDA(cudaMemcpyAsync(didx, indices, n_idx * 4, cudaMemcpyHostToDevice, s));
     {
       LaunchScope ls(c, "gather_rows", 0, 2.0 * n_idx * K);
-      launch_gather_rows(dW, dpb, dc, didx, static_cast<int>(n_idx), static_cast<int>(K), dWs, dpbs, dcs, s);
+      launch_gather_rows(dW, dpb, didx, static_cast<int>(n_idx), static_cast<int>(K), dWs, dpbs, s);
     }
-    Wuse = dWs, pbuse = dpbs, cuse = dcs;
+    Wuse = dWs, pbuse = dpbs;
   }
   QuantOuts q = qouts();
   qadd(q, dqa, aq);
@@ -505,14 +496,14 @@ int qmm_affine_host(Context& c, const float* x, size_t M, size_t K, const int8_t
   const float um = 1.0f / (aq * bq);
   {
     GemmCall g(&c, "qmm_affine_gemm", static_cast<int>(M), static_cast<int>(Nout), static_cast<int>(K), EPI_F32);
-    GemmProblem* p = g.add(dqa, Wuse, cuse, pbuse, um);
+    GemmProblem* p = g.add(dqa, Wuse, pbuse, um);
     if (!p) return 1;
     p->out = dy, p->ldo = static_cast<int>(Nout);
     if (g.launch()) return 1;
   }
   if (acc_out) {
     GemmCall g(&c, "qmm_acc_gemm", static_cast<int>(M), static_cast<int>(Nout), static_cast<int>(K), EPI_ACC);
-    GemmProblem* p = g.add(dqa, Wuse, cuse, pbuse, um);
+    GemmProblem* p = g.add(dqa, Wuse, pbuse, um);
     if (!p) return 1;
     p->out = dacc, p->ldo = static_cast<int>(Nout);
     if (g.launch()) return 1;
@@ -522,6 +513,9 @@ int qmm_affine_host(Context& c, const float* x, size_t M, size_t K, const int8_t
   SB_CUDA(cudaMemcpyAsync(y, dy, M * Nout * 4, cudaMemcpyDeviceToHost, s));
   c.d2h_bytes += M * Nout * 4;
   SB_CUDA(cudaStreamSynchronize(s));
+  if (qa_out) {
+    for (size_t i = 0; i < M * K; i++) qa_out[i] = static_cast<int8_t>(static_cast<int>(static_cast<uint8_t>(qa_out[i])) - 127);
+  }
   return 0;
 }
 
@@ -736,7 +730,6 @@ int model_forward(Model& m, ForwardArgs& a) {
   const uint32_t* d_sl = nullptr;
   const int8_t* Wout = m.out.w;
   const float* pb_out = m.out.pb;
-  const int32_t* c127_out = m.out.c127;
   if (use_sl) {
     if (a.device_io) {
       d_sl = a.shortlist;
@@ -750,12 +743,11 @@ int model_forward(Model& m, ForwardArgs& a) {
     // SelectColumnsB + bias gather, once per batch (qmm/Intgemm.inl.cc:49-66)
     int8_t* Ws = c.take<int8_t>(static_cast<size_t>(Nout) * E);
     float* pbs = c.take<float>(Nout);
-    int32_t* cs = c.take<int32_t>(Nout);
     {
       LaunchScope ls(c, "gather_rows", 0, 2.0 * Nout * E);
-      launch_gather_rows(m.out.w, m.out.pb, m.out.c127, d_sl, Nout, E, Ws, pbs, cs, s);
+      launch_gather_rows(m.out.w, m.out.pb, d_sl, Nout, E, Ws, pbs, s);
     }
-    Wout = Ws, pb_out = pbs, c127_out = cs;
+    Wout = Ws, pb_out = pbs;
   }
   float* d_logits = a.logits ? c.take<float>(static_cast<size_t>(B) * Nout) : nullptr;
   float* d_align = a.alignment ? c.take<float>(static_cast<size_t>(B) * T) : nullptr;
@@ -848,7 +840,7 @@ int model_forward(Model& m, ForwardArgs& a) {
     // output projection (+ shortlist) and greedy choice (Transformer.cc:176-182, 279-339)
     if (d_logits) {
       GemmCall g(&c, "dec_gemm_out_logits", B, Nout, E, EPI_F32);
-      GemmProblem* p = g.add(oq, Wout, c127_out, pb_out, m.out.um);
+      GemmProblem* p = g.add(oq, Wout, pb_out, m.out.um);
       if (!p) return 1;
       p->out = d_logits, p->ldo = Nout;
       if (g.launch()) return 1;
@@ -861,7 +853,7 @@ int model_forward(Model& m, ForwardArgs& a) {
       c.d2h_bytes += 4ul * B * Nout;
     } else {
       GemmCall g(&c, "dec_gemm_out_argmax", B, Nout, E, EPI_ARGMAX);
-      GemmProblem* p = g.add(oq, Wout, c127_out, pb_out, m.out.um);
+      GemmProblem* p = g.add(oq, Wout, pb_out, m.out.um);
       if (!p) return 1;
       p->best = best;
       if (g.launch()) return 1;

@@ -96,7 +96,6 @@ struct DevWeight {
   int K = 0, N = 0;
   float aq = 0, bq = 0, um = 0;
   int8_t* w = nullptr;      // [N][K]
-  int32_t* c127 = nullptr;  // [N]
   float* pb = nullptr;      // [N]
 };
 
@@ -165,8 +164,7 @@ int qmm_affine_host(Context& c, const float* x, size_t M, size_t K, const int8_t
                     int32_t* acc_out);
 
 // Host-side exact helpers shared by loader and operator API
-void host_prepare_bias(const int8_t* Bt, const float* bias, float aq, float bq, size_t K, size_t N, float* pb,
-                       int32_t* c127);
+void host_prepare_bias(const int8_t* Bt, const float* bias, float aq, float bq, size_t K, size_t N, float* pb);
 void host_quantize(const float* x, int8_t* q, float mult, size_t n);
 
 }  // namespace sb

@@ -50,8 +50,7 @@ __global__ void __launch_bounds__(kThreads) gemm_i8_kernel(const __grid_constant
   uint64_t* accum_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
   float* s_pb = reinterpret_cast<float*>(tail + 128);
-  int32_t* s_c127 = reinterpret_cast<int32_t*>(s_pb + BN);
-  float* s_scale = reinterpret_cast<float*>(s_c127 + BN);
+  float* s_scale = s_pb + BN;
   float* s_bias = s_scale + BN;
 
   const int warp = threadIdx.x >> 5;
@@ -77,7 +76,6 @@ __global__ void __launch_bounds__(kThreads) gemm_i8_kernel(const __grid_constant
       int n = n0 + i;
       bool ok = n < N;
       s_pb[i] = ok ? P.pb[n] : 0.0f;
-      s_c127[i] = ok ? P.c127[n] : 0;
       if constexpr (EPI == EPI_RES_LN) {
         s_scale[i] = ok ? P.ln_scale[n] : 0.0f;
         s_bias[i] = ok ? P.ln_bias[n] : 0.0f;
@@ -150,8 +148,7 @@ __global__ void __launch_bounds__(kThreads) gemm_i8_kernel(const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (nb + j < N) {
-                int4 w = make_int4((int)v[j] + s_c127[c * 32 + j], (int)v[j + 1] + s_c127[c * 32 + j + 1],
-                                   (int)v[j + 2] + s_c127[c * 32 + j + 2], (int)v[j + 3] + s_c127[c * 32 + j + 3]);
+                int4 w = make_int4((int)v[j], (int)v[j + 1], (int)v[j + 2], (int)v[j + 3]);
                 *reinterpret_cast<int4*>(o + j) = w;
               }
             }
@@ -163,7 +160,7 @@ __global__ void __launch_bounds__(kThreads) gemm_i8_kernel(const __grid_constant
                 float y[4];
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
-                  y[e] = dequant1((int)v[j + e] + s_c127[c * 32 + j + e], um, s_pb[c * 32 + j + e]);
+                  y[e] = dequant1((int)v[j + e], um, s_pb[c * 32 + j + e]);
                   if (P.relu) y[e] = y[e] > 0.0f ? y[e] : 0.0f;  // std::max<float>(0, a), TensorOps.cc:163
                 }
                 *reinterpret_cast<float4*>(o + j) = make_float4(y[0], y[1], y[2], y[3]);
@@ -185,7 +182,7 @@ __global__ void __launch_bounds__(kThreads) gemm_i8_kernel(const __grid_constant
             int qv[4];
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-              float y = dequant1((int)v[j + e] + s_c127[c * 32 + j + e], um, s_pb[c * 32 + j + e]);
+              float y = dequant1((int)v[j + e], um, s_pb[c * 32 + j + e]);
               if (P.relu) y = y > 0.0f ? y : 0.0f;
               qv[e] = quantize1(y, aq);
             }
@@ -214,7 +211,7 @@ __global__ void __launch_bounds__(kThreads) gemm_i8_kernel(const __grid_constant
           float r[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
           for (int e = 0; e < 4; e++) {
-            float y = dequant1((int)v[j + e] + s_c127[c * 32 + j + e], um, s_pb[c * 32 + j + e]);
+            float y = dequant1((int)v[j + e], um, s_pb[c * 32 + j + e]);
             float x = __fadd_rn(y, r[e]);
             sum = __fadd_rn(sum, x);
             v[j + e] = __float_as_uint(x);
@@ -274,7 +271,7 @@ __global__ void __launch_bounds__(kThreads) gemm_i8_kernel(const __grid_constant
         const int nb = n0 + c * 32;
 #pragma unroll
         for (int j = 0; j < 32; j++) {
-          float y = dequant1((int)v[j] + s_c127[c * 32 + j], um, s_pb[c * 32 + j]);
+          float y = dequant1((int)v[j], um, s_pb[c * 32 + j]);
           bool valid = nb + j < N;
           if (valid && (!have || y > best)) {
             best = y;
@@ -329,8 +326,8 @@ void dispatch_bn(const GemmBatch& b, int n_problems, int BN, cudaStream_t stream
 }  // namespace
 
 size_t gemm_smem_bytes(int BN, int stages) {
-  // stages * (A + B) + barriers (128 B) + pb/c127/scale/bias (16 B per column) + 1024 B alignment slack
-  return static_cast<size_t>(stages) * (kBM * kBK + BN * kBK) + 128 + static_cast<size_t>(BN) * 16 + 1024;
+  // stages * (A + B) + barriers (128 B) + pb/scale/bias (12 B per column) + 1024 B alignment slack
+  return static_cast<size_t>(stages) * (kBM * kBK + BN * kBK) + 128 + static_cast<size_t>(BN) * 12 + 1024;
 }
 
 void launch_gemm_i8(const GemmBatch& batch, int n_problems, int epilogue, int BN, cudaStream_t stream) {

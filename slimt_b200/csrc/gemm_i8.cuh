@@ -8,7 +8,8 @@
 // MMA, UnquantizeAndAddBiasAndWrite (+ReLU / +requantize / +residual+LayerNorm /
 // +argmax) is the epilogue.
 //
-// Layouts: A = quantized activations qa, int8 [M][K] row-major (K contiguous);
+// Layouts: A = quantized activations as the reference's PrepareA emits them, u8 = qa + 127, [M][K] row-major
+// (K contiguous), so the u8 x s8 MMA forms Int8Shift::Multiply's shifted accumulator directly;
 // B = weights in the STORED model layout B^T, int8 [N][K] (K contiguous) -- i.e.
 // both operands are "K-major" for UMMA, no re-tiling at load.  One CTA computes
 // one [128 x BN] output tile; K is consumed in 128-byte blocks (one 128B-swizzle
@@ -35,7 +36,6 @@ enum Epilogue : int {
 struct GemmProblem {
   CUtensorMap tma_a;  // int8 [M][K]
   CUtensorMap tma_b;  // int8 [N][K]
-  const int32_t* c127;  // [N] 127 * colsum(B): restores the reference's +127 shift exactly
   const float* pb;      // [N] prepared bias: colsum*(-127/(aq*bq)) + bias  (Intgemm.inl.cc:112-128)
   float um;             // 1/(aq*bq)
   int relu;

@@ -214,8 +214,8 @@ __global__ void finalize_step_kernel(unsigned long long* __restrict__ best, cons
 }
 
 __global__ void gather_rows_kernel(const int8_t* __restrict__ W, const float* __restrict__ pb,
-                                   const int32_t* __restrict__ c127, const uint32_t* __restrict__ idx, int K,
-                                   int8_t* __restrict__ W_sel, float* __restrict__ pb_sel, int32_t* __restrict__ c127_sel) {
+                                   const uint32_t* __restrict__ idx, int K, int8_t* __restrict__ W_sel,
+                                   float* __restrict__ pb_sel) {
   const int i = blockIdx.x;
   const uint32_t src = idx[i];
   const uint4* s = reinterpret_cast<const uint4*>(W + static_cast<size_t>(src) * K);
@@ -223,7 +223,6 @@ __global__ void gather_rows_kernel(const int8_t* __restrict__ W, const float* __
   for (int t = threadIdx.x; t < K / 16; t += blockDim.x) d[t] = s[t];
   if (threadIdx.x == 0) {
     pb_sel[i] = pb[src];
-    c127_sel[i] = c127[src];
   }
 }
 
@@ -302,10 +301,10 @@ void launch_finalize_step(unsigned long long* best, const uint32_t* shortlist, c
                                              sqrt_e, pos0, B, E, x, q);
 }
 
-void launch_gather_rows(const int8_t* W, const float* pb, const int32_t* c127, const uint32_t* idx, int n_idx, int K,
-                        int8_t* W_sel, float* pb_sel, int32_t* c127_sel, cudaStream_t stream) {
+void launch_gather_rows(const int8_t* W, const float* pb, const uint32_t* idx, int n_idx, int K, int8_t* W_sel,
+                        float* pb_sel, cudaStream_t stream) {
   if (n_idx == 0) return;
-  gather_rows_kernel<<<n_idx, 32, 0, stream>>>(W, pb, c127, idx, K, W_sel, pb_sel, c127_sel);
+  gather_rows_kernel<<<n_idx, 32, 0, stream>>>(W, pb, idx, K, W_sel, pb_sel);
 }
 
 void launch_argmax_rows(const float* logits, int rows, int cols, unsigned long long* best, cudaStream_t stream) {

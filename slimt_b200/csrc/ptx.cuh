@@ -141,7 +141,7 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 //   [4,6) c_format=2 (S32)  [7,10) a_format=1 (INT8)  [10,13) b_format=1 (INT8)
 //   [15] a_major=0  [16] b_major=0  [17,23) N>>3  [24,29) M>>4
 __host__ __device__ constexpr uint32_t make_idesc_i8(uint32_t M, uint32_t N) {
-  return (2u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+  return (2u << 4) | (0u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 }  // namespace sb
