@@ -749,6 +749,8 @@ int model_forward(Model& m, ForwardArgs& a) {
     }
     Wout = Ws, pb_out = pbs;
   }
+  CUtensorMap map_oq, map_wout;
+  if (c.make_map(&map_oq, oq, B, E, kBM) || c.make_map(&map_wout, Wout, Nout, E, 256)) return 1;
   float* d_logits = a.logits ? c.take<float>(static_cast<size_t>(B) * Nout) : nullptr;
   float* d_align = a.alignment ? c.take<float>(static_cast<size_t>(B) * T) : nullptr;
 
@@ -852,11 +854,12 @@ int model_forward(Model& m, ForwardArgs& a) {
                               cudaMemcpyDeviceToHost, s));
       c.d2h_bytes += 4ul * B * Nout;
     } else {
-      GemmCall g(&c, "dec_gemm_out_argmax", B, Nout, E, EPI_ARGMAX);
-      GemmProblem* p = g.add(oq, Wout, pb_out, m.out.um);
-      if (!p) return 1;
-      p->best = best;
-      if (g.launch()) return 1;
+      const double Md = B, Nd = Nout, Kd = E;
+      LaunchScope ls(c, "dec_gemm_out_argmax", 2.0 * Md * Nd * Kd, Md * Kd + Nd * Kd + 4.0 * Nd + 8.0 * Md);
+      if (launch_gemm_out_argmax(map_oq, map_wout, pb_out, m.out.um, B, Nout, E, best, c.num_sms, s)) {
+        set_error("output GEMM: unsupported K " + std::to_string(E));
+        return 1;
+      }
     }
     if (d_align) {
       SB_CUDA(cudaMemcpyAsync(a.alignment + static_cast<size_t>(step) * B * T, d_align, 4ul * B * T,

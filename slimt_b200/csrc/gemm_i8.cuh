@@ -65,4 +65,10 @@ size_t gemm_smem_bytes(int BN, int stages);
 // Launches grid (ceil(N/BN), ceil(M/128), n_problems).
 void launch_gemm_i8(const GemmBatch& batch, int n_problems, int epilogue, int BN, cudaStream_t stream);
 
+// Output projection fused with greedy argmax (gemm_out.cu).  tma_a: u8 [M][K] with box {128 B, 128 rows};
+// tma_b: s8 [N][K] with box {128 B, 256 rows}; best [M] packed (ordered value << 32 | ~index), pre-zeroed.
+// Returns nonzero for an unsupported K (128 * {2, 4} are built).
+int launch_gemm_out_argmax(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const float* pb, float um, int M, int N,
+                           int K, unsigned long long* best, int num_sms, cudaStream_t stream);
+
 }  // namespace sb

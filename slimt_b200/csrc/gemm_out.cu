@@ -1,0 +1,233 @@
+// Output projection fused with the greedy choice (reference: Decoder::step's affine /
+// affine_with_select on Wemb, slimt/Transformer.cc:176-182, followed by greedy_sample /
+// greedy_sample_from_words, :279-339).  [M rows] x [N vocabulary or shortlist columns], K = E.
+//
+// Persistent warp-specialised tcgen05 kernel: one CTA per SM walks a contiguous range of
+// [128 x 256] output tiles in column-major tile order.  The weight tile (B, 256 columns x K) stays
+// resident in shared memory for a whole run of row tiles -- it is the larger operand, so this halves
+// the L2 -> SM traffic -- while the u8 activation tiles (A, 128 rows x 128-byte k-blocks) stream
+// through a TMA/mbarrier ring; accumulators are double-buffered in TMEM (2 x 256 columns) so the MMAs
+// of tile i+1 overlap the epilogue of tile i.  Eight epilogue warps (TMEM lane quadrant x column half)
+// dequantise exactly like UnquantizeAndAddBiasAndWrite, reduce their 128 columns to a first-maximum
+// per row and publish (value, lowest index) with a filtered 64-bit atomicMax.
+#include <stdio.h>
+
+#include "exact_math.cuh"
+#include "gemm_i8.cuh"
+#include "ptx.cuh"
+
+namespace sb {
+
+namespace {
+
+constexpr int kOutBN = 256;
+constexpr int kOutStages = 6;
+constexpr int kOutThreads = 384;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 epilogue
+
+__device__ __forceinline__ unsigned long long pack_best_out(float v, uint32_t idx) {
+  if (v == 0.0f) v = 0.0f;  // canonicalise -0 so equal values compare equal
+  uint32_t b = __float_as_uint(v);
+  uint32_t key = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return (static_cast<unsigned long long>(key) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - idx);
+}
+
+template <int KB>  // K = 128 * KB bytes per row
+__global__ void __launch_bounds__(kOutThreads, 1)
+    out_argmax_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                      const float* __restrict__ pb, float um, int M, int N, unsigned long long* __restrict__ best) {
+  constexpr int kABytes = kBM * kBK;        // one k-block of A
+  constexpr int kBBytes = kOutBN * kBK;     // one k-block of B
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = smem;                     // resident weight tile: KB k-blocks
+  uint8_t* smem_a = smem + KB * kBBytes;      // ring of activation k-blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + kOutStages * kABytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kOutStages;
+  uint64_t* b_full = bars + 2 * kOutStages;
+  uint64_t* b_empty = b_full + 1;
+  uint64_t* tmem_full = b_empty + 1;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (N + kOutBN - 1) / kOutBN;
+  const int m_tiles = (M + kBM - 1) / kBM;
+  const long total = static_cast<long>(n_tiles) * m_tiles;
+  const int t_begin = static_cast<int>(total * blockIdx.x / gridDim.x);
+  const int t_end = static_cast<int>(total * (blockIdx.x + 1) / gridDim.x);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kOutStages; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(b_full, 1);
+    mbar_init(b_empty, 1);
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      uint32_t kbc = 0;  // running k-block counter (ring position)
+      uint32_t run = 0;  // running count of column-tile runs
+      int cur_n = -1;
+      for (int t = t_begin; t < t_end; t++) {
+        const int n = t / m_tiles, m = t % m_tiles;
+        if (n != cur_n) {
+          mbar_wait(b_empty, (run & 1) ^ 1);
+          mbar_expect_tx(b_full, KB * kBBytes);
+#pragma unroll
+          for (int kb = 0; kb < KB; kb++) tma_load_2d(smem_b + kb * kBBytes, &tma_b, b_full, kb * kBK, n * kOutBN);
+          cur_n = n;
+          run++;
+        }
+#pragma unroll
+        for (int kb = 0; kb < KB; kb++, kbc++) {
+          const uint32_t s = kbc % kOutStages;
+          const uint32_t ph = (kbc / kOutStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], kABytes);
+          tma_load_2d(smem_a + s * kABytes, &tma_a, &full_bar[s], kb * kBK, m * kBM);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread) =====
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_i8(kBM, kOutBN);
+      uint32_t kbc = 0, run = 0, i = 0;
+      int cur_n = -1;
+      for (int t = t_begin; t < t_end; t++, i++) {
+        const int n = t / m_tiles;
+        if (n != cur_n) {
+          mbar_wait(b_full, run & 1);
+          cur_n = n;
+          run++;
+        }
+        const uint32_t buf = i & 1;
+        mbar_wait(&tmem_empty[buf], ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < KB; kb++, kbc++) {
+          const uint32_t s = kbc % kOutStages;
+          const uint32_t ph = (kbc / kOutStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + s * kABytes));
+          const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + kb * kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBK / 32; k++) {
+            umma_i8(tmem_base + buf * kOutBN, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full[buf]);
+        const bool last_of_run = (t + 1 == t_end) || ((t + 1) / m_tiles != n);
+        if (last_of_run) umma_commit(b_empty);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: thread <-> TMEM lane <-> output row; warps split the 256 columns in halves =====
+    const int e = warp - 4;
+    const int q = warp & 3;
+    const int half = e >> 2;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t i = 0;
+    for (int t = t_begin; t < t_end; t++, i++) {
+      const int n = t / m_tiles, m = t % m_tiles;
+      const uint32_t buf = i & 1;
+      mbar_wait(&tmem_full[buf], (i >> 1) & 1);
+      tc_fence_after();
+      const int n0 = n * kOutBN + half * 128;
+      float bv = 0.0f;
+      uint32_t bi = 0;
+      bool have = false;
+#pragma unroll 1
+      for (int c = 0; c < 4; c++) {
+        const int nb = n0 + c * 32;
+        if (nb >= N) break;
+        uint32_t v[32];
+        tmem_ld32(lane_addr + buf * kOutBN + half * 128 + c * 32, v);
+        float y[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const bool ok = nb + j < N;  // N % 8 == 0: groups of four are entirely inside or outside
+          if (ok) p4 = __ldg(reinterpret_cast<const float4*>(pb + nb + j));
+          y[j] = dequant1(static_cast<int>(v[j]), um, p4.x);
+          y[j + 1] = dequant1(static_cast<int>(v[j + 1]), um, p4.y);
+          y[j + 2] = dequant1(static_cast<int>(v[j + 2]), um, p4.z);
+          y[j + 3] = dequant1(static_cast<int>(v[j + 3]), um, p4.w);
+          if (!ok) y[j] = y[j + 1] = y[j + 2] = y[j + 3] = -__int_as_float(0x7f800000);
+        }
+        float mx = y[0];
+#pragma unroll
+        for (int j = 1; j < 32; j++) mx = fmaxf(mx, y[j]);
+        if (!have || mx > bv) {
+          // first column of the chunk that attains the maximum (greedy_sample keeps the first strict max)
+          int idx = 31;
+#pragma unroll
+          for (int j = 30; j >= 0; j--) idx = (y[j] == mx) ? j : idx;
+          bv = mx;
+          bi = static_cast<uint32_t>(nb + idx);
+          have = true;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      const int row = m * kBM + q * 32 + lane;
+      if (row < M && have) {
+        // `best` only grows: a stale read can only cause a redundant atomic, never a missed one
+        const unsigned long long key = pack_best_out(bv, bi);
+        if (key > __ldcg(best + row)) atomicMax(best + row, key);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+size_t out_smem_bytes(int KB) { return static_cast<size_t>(KB) * kOutBN * kBK + kOutStages * kBM * kBK + 256 + 1024; }
+
+}  // namespace
+
+int launch_gemm_out_argmax(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const float* pb, float um, int M, int N,
+                           int K, unsigned long long* best, int num_sms, cudaStream_t stream) {
+  const int KB = K / kBK;
+  const long tiles = static_cast<long>((M + kBM - 1) / kBM) * ((N + kOutBN - 1) / kOutBN);
+  const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
+  if (grid == 0) return 0;
+  const size_t smem = out_smem_bytes(KB);
+  if (KB == 2) {
+    auto kern = out_argmax_kernel<2>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    kern<<<grid, kOutThreads, smem, stream>>>(tma_a, tma_b, pb, um, M, N, best);
+  } else if (KB == 4) {
+    auto kern = out_argmax_kernel<4>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    kern<<<grid, kOutThreads, smem, stream>>>(tma_a, tma_b, pb, um, M, N, best);
+  } else {
+    return 1;
+  }
+  return 0;
+}
+
+}  // namespace sb
