@@ -330,6 +330,24 @@ int Model::load(Context* c, const void* bin, size_t bytes, int enc_layers, int d
     std::vector<int8_t> req(deq.size());
     host_quantize(deq.data(), req.data(), emb_qm, deq.size());
     if (weight("Wemb", "decoder_ff_logit_out_b", out, req.data(), "none_QuantMultA")) return 1;
+    // bound filter of the fused output GEMM: 127 * colsum per column, per-chunk dmax, rounding slack eta
+    std::vector<int32_t> c127(V);
+    for (int n = 0; n < V; n++) {
+      int32_t cs = 0;
+      for (int k = 0; k < E; k++) cs += req[static_cast<size_t>(n) * E + k];
+      c127[n] = 127 * cs;
+    }
+    if (upload(c127.data(), 4ul * V, reinterpret_cast<void**>(&out.c127))) return 1;
+    SB_CUDA(cudaMalloc(&out.dmax, 4ul * ((V + 31) / 32)));
+    owned.push_back(out.dmax);
+    launch_out_bounds(out.c127, out.pb, out.um, V, out.dmax, c->stream);
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<float> pbh(V);
+    SB_CUDA(cudaMemcpy(pbh.data(), out.pb, 4ul * V, cudaMemcpyDeviceToHost));
+    double pbabs = 0;
+    for (float v : pbh) pbabs = std::max(pbabs, static_cast<double>(fabsf(v)));
+    const double vmax = static_cast<double>(E) * 254.0 * 128.0;
+    out.eta = static_cast<float>((2.0 * vmax * out.um + pbabs) * ldexp(1.0, -22));
   }
 
   enc.resize(enc_layers);
@@ -483,7 +501,7 @@ int qmm_affine_host(Context& c, const float* x, size_t M, size_t K, const int8_t
     SB_CUDA(cudaMemcpyAsync(didx, indices, n_idx * 4, cudaMemcpyHostToDevice, s));
     {
       LaunchScope ls(c, "gather_rows", 0, 2.0 * n_idx * K);
-      launch_gather_rows(dW, dpb, didx, static_cast<int>(n_idx), static_cast<int>(K), dWs, dpbs, s);
+      launch_gather_rows(dW, dpb, nullptr, didx, static_cast<int>(n_idx), static_cast<int>(K), dWs, dpbs, nullptr, s);
     }
     Wuse = dWs, pbuse = dpbs;
   }
@@ -567,7 +585,7 @@ int model_forward(Model& m, ForwardArgs& a) {
   acc(8ul * B), acc(B), acc(4ul * B), acc(256);                 // best, done, tgt_len, counters
   acc(4ul * std::max(1, max_steps) * B);                        // step tokens
   if (a.forced) acc(4ul * std::max(1, max_steps) * B);
-  if (use_sl) acc(4ul * Nout), acc(1ul * Nout * E), acc(4ul * Nout), acc(4ul * Nout);
+  if (use_sl) acc(4ul * Nout), acc(1ul * Nout * E), acc(4ul * Nout), acc(4ul * Nout), acc(4ul * (Nout / 32 + 1));
   if (a.logits) acc(4ul * B * Nout);
   if (a.alignment) acc(4ul * B * T);
   need += 64 * 256;
@@ -730,6 +748,8 @@ int model_forward(Model& m, ForwardArgs& a) {
   const uint32_t* d_sl = nullptr;
   const int8_t* Wout = m.out.w;
   const float* pb_out = m.out.pb;
+  const int32_t* c127_out = m.out.c127;
+  const float* dmax_out = m.out.dmax;
   if (use_sl) {
     if (a.device_io) {
       d_sl = a.shortlist;
@@ -743,11 +763,17 @@ int model_forward(Model& m, ForwardArgs& a) {
     // SelectColumnsB + bias gather, once per batch (qmm/Intgemm.inl.cc:49-66)
     int8_t* Ws = c.take<int8_t>(static_cast<size_t>(Nout) * E);
     float* pbs = c.take<float>(Nout);
+    int32_t* cs = c.take<int32_t>(Nout);
+    float* dms = c.take<float>(Nout / 32 + 1);
     {
       LaunchScope ls(c, "gather_rows", 0, 2.0 * Nout * E);
-      launch_gather_rows(m.out.w, m.out.pb, d_sl, Nout, E, Ws, pbs, s);
+      launch_gather_rows(m.out.w, m.out.pb, m.out.c127, d_sl, Nout, E, Ws, pbs, cs, s);
     }
-    Wout = Ws, pb_out = pbs;
+    {
+      LaunchScope ls(c, "out_bounds", 0, 8.0 * Nout);
+      launch_out_bounds(cs, pbs, m.out.um, Nout, dms, s);
+    }
+    Wout = Ws, pb_out = pbs, c127_out = cs, dmax_out = dms;
   }
   CUtensorMap map_oq, map_wout;
   if (c.make_map(&map_oq, oq, B, E, kBM) || c.make_map(&map_wout, Wout, Nout, E, 256)) return 1;
@@ -830,6 +856,7 @@ int model_forward(Model& m, ForwardArgs& a) {
         if (last) {
           p->out = nullptr;
           padd(p, oq, m.out.aq);
+          if (!a.logits) p->qout_signed = 1;  // the fused argmax GEMM takes the signed qa (gemm_out.cu)
         } else {
           p->out = zb[l & 1];
           padd(p, zq[0], m.dec[l + 1].rnn_wf.aq), padd(p, zq[1], m.dec[l + 1].rnn_w.aq);
@@ -856,7 +883,8 @@ int model_forward(Model& m, ForwardArgs& a) {
     } else {
       const double Md = B, Nd = Nout, Kd = E;
       LaunchScope ls(c, "dec_gemm_out_argmax", 2.0 * Md * Nd * Kd, Md * Kd + Nd * Kd + 4.0 * Nd + 8.0 * Md);
-      if (launch_gemm_out_argmax(map_oq, map_wout, pb_out, m.out.um, B, Nout, E, best, c.num_sms, s)) {
+      if (launch_gemm_out_argmax(map_oq, map_wout, pb_out, c127_out, dmax_out, m.out.um, m.out.eta, B, Nout, E, best,
+                                 c.num_sms, s)) {
         set_error("output GEMM: unsupported K " + std::to_string(E));
         return 1;
       }

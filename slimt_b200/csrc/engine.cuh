@@ -97,6 +97,10 @@ struct DevWeight {
   float aq = 0, bq = 0, um = 0;
   int8_t* w = nullptr;      // [N][K]
   float* pb = nullptr;      // [N]
+  // output layer only: inputs of the fused argmax GEMM's bound filter (gemm_out.cu)
+  int32_t* c127 = nullptr;  // [N] 127 * colsum
+  float* dmax = nullptr;    // [ceil(N/32)]
+  float eta = 0;            // slack covering the float roundings of the exact epilogue
 };
 
 struct DevLN {

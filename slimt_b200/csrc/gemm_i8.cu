@@ -249,10 +249,12 @@ __global__ void __launch_bounds__(kThreads) gemm_i8_kernel(const __grid_constant
           }
           for (int k = 0; k < P.n_qout; k++) {
             const float aq = P.aq_out[k];
+            const int sh = ((P.qout_signed >> k) & 1) ? 127 : 0;
             uint32_t w[8];
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-              w[j / 4] = pack4(quantize1(y[j], aq), quantize1(y[j + 1], aq), quantize1(y[j + 2], aq), quantize1(y[j + 3], aq));
+              w[j / 4] = pack4(quantize1(y[j], aq) - sh, quantize1(y[j + 1], aq) - sh, quantize1(y[j + 2], aq) - sh,
+                               quantize1(y[j + 3], aq) - sh);
             int8_t* o = P.qout[k] + static_cast<size_t>(row) * N + c * 32;
             *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4*>(o + 16) = make_uint4(w[4], w[5], w[6], w[7]);

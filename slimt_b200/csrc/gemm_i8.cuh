@@ -46,6 +46,7 @@ struct GemmProblem {
   int8_t* qout[kMaxQuantOut];
   float aq_out[kMaxQuantOut];
   int n_qout;
+  int qout_signed;  // bit k set: qout[k] receives the signed qa instead of the u8 (qa + 127)
   // EPI_RES_LN
   const float* residual;  // f32 [M][N]
   const float* ln_scale;  // [N]
@@ -65,10 +66,12 @@ size_t gemm_smem_bytes(int BN, int stages);
 // Launches grid (ceil(N/BN), ceil(M/128), n_problems).
 void launch_gemm_i8(const GemmBatch& batch, int n_problems, int epilogue, int BN, cudaStream_t stream);
 
-// Output projection fused with greedy argmax (gemm_out.cu).  tma_a: u8 [M][K] with box {128 B, 128 rows};
-// tma_b: s8 [N][K] with box {128 B, 256 rows}; best [M] packed (ordered value << 32 | ~index), pre-zeroed.
+// Output projection fused with greedy argmax (gemm_out.cu).  tma_a: SIGNED s8 activations [M][K] with box
+// {128 B, 128 rows}; tma_b: s8 [N][K] with box {128 B, 256 rows}; c127 [N] = 127 * colsum(B); dmax
+// [ceil(N/32)] and eta from launch_out_bounds; best [M] packed (ordered value << 32 | ~index), pre-zeroed.
 // Returns nonzero for an unsupported K (128 * {2, 4} are built).
-int launch_gemm_out_argmax(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const float* pb, float um, int M, int N,
-                           int K, unsigned long long* best, int num_sms, cudaStream_t stream);
+int launch_gemm_out_argmax(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const float* pb, const int32_t* c127,
+                           const float* dmax, float um, float eta, int M, int N, int K, unsigned long long* best,
+                           int num_sms, cudaStream_t stream);
 
 }  // namespace sb

@@ -8,8 +8,17 @@
 // the L2 -> SM traffic -- while the u8 activation tiles (A, 128 rows x 128-byte k-blocks) stream
 // through a TMA/mbarrier ring; accumulators are double-buffered in TMEM (2 x 256 columns) so the MMAs
 // of tile i+1 overlap the epilogue of tile i.  Eight epilogue warps (TMEM lane quadrant x column half)
-// dequantise exactly like UnquantizeAndAddBiasAndWrite, reduce their 128 columns to a first-maximum
-// per row and publish (value, lowest index) with a filtered 64-bit atomicMax.
+// reduce their 128 columns to a first-maximum per row and publish (value, lowest index) with a
+// filtered 64-bit atomicMax.
+//
+// Epilogue arithmetic.  The exact logit is y = fl(fl(float(v) * um) + pb[n]) with v the SHIFTED
+// accumulator sum_k (qa+127)*B (UnquantizeAndAddBiasAndWrite).  Here A is the SIGNED qa, so TMEM holds
+// v' = v - c127[n] (c127 = 127 * colsum(B), exact).  Per 32-column chunk the warp first forms an upper
+// bound of every y in the chunk from integer data only:  ub = ru(float(max v') * um + dmax) + eta, where
+// dmax = max_n (c127[n] * um + pb[n]) rounded up (precomputed per chunk) and eta covers the float
+// roundings of the exact formula.  Only when ub can reach the row's best so far (read back from `best`,
+// which other CTAs keep raising) are the 32 exact logits evaluated; a skipped chunk cannot contain the
+// maximum, so the result is still the reference's first strict maximum.
 #include <stdio.h>
 
 #include "exact_math.cuh"
@@ -34,7 +43,8 @@ __device__ __forceinline__ unsigned long long pack_best_out(float v, uint32_t id
 template <int KB>  // K = 128 * KB bytes per row
 __global__ void __launch_bounds__(kOutThreads, 1)
     out_argmax_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                      const float* __restrict__ pb, float um, int M, int N, unsigned long long* __restrict__ best) {
+                      const float* __restrict__ pb, const int32_t* __restrict__ c127, const float* __restrict__ dmax,
+                      float um, float eta, int M, int N, unsigned long long* __restrict__ best) {
   constexpr int kABytes = kBM * kBK;        // one k-block of A
   constexpr int kBBytes = kOutBN * kBK;     // one k-block of B
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -109,7 +119,7 @@ __global__ void __launch_bounds__(kOutThreads, 1)
   } else if (warp == 1) {
     // ===== MMA issuer (single thread) =====
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_i8(kBM, kOutBN);
+      constexpr uint32_t idesc = make_idesc_i8(kBM, kOutBN) | (1u << 7);  // A signed: s8 x s8
       uint32_t kbc = 0, run = 0, i = 0;
       int cur_n = -1;
       for (int t = t_begin; t < t_end; t++, i++) {
@@ -154,6 +164,14 @@ __global__ void __launch_bounds__(kOutThreads, 1)
       mbar_wait(&tmem_full[buf], (i >> 1) & 1);
       tc_fence_after();
       const int n0 = n * kOutBN + half * 128;
+      const int row = m * kBM + q * 32 + lane;
+      // the row's best so far, from any CTA (monotone: a stale value only weakens the filter)
+      const unsigned long long seen = row < M ? __ldcg(best + row) : ~0ull;
+      float thr = -__int_as_float(0x7f800000);
+      if (seen != 0ull) {
+        const uint32_t key = static_cast<uint32_t>(seen >> 32);
+        thr = __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+      }
       float bv = 0.0f;
       uint32_t bi = 0;
       bool have = false;
@@ -163,39 +181,47 @@ __global__ void __launch_bounds__(kOutThreads, 1)
         if (nb >= N) break;
         uint32_t v[32];
         tmem_ld32(lane_addr + buf * kOutBN + half * 128 + c * 32, v);
-        float y[32];
+        int vm = static_cast<int>(v[0]);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          const bool ok = nb + j < N;  // N % 8 == 0: groups of four are entirely inside or outside
-          if (ok) p4 = __ldg(reinterpret_cast<const float4*>(pb + nb + j));
-          y[j] = dequant1(static_cast<int>(v[j]), um, p4.x);
-          y[j + 1] = dequant1(static_cast<int>(v[j + 1]), um, p4.y);
-          y[j + 2] = dequant1(static_cast<int>(v[j + 2]), um, p4.z);
-          y[j + 3] = dequant1(static_cast<int>(v[j + 3]), um, p4.w);
-          if (!ok) y[j] = y[j + 1] = y[j + 2] = y[j + 3] = -__int_as_float(0x7f800000);
-        }
-        float mx = y[0];
+        for (int j = 1; j < 32; j += 2) vm = max(vm, max(static_cast<int>(v[j]), static_cast<int>(v[j + 1 < 32 ? j + 1 : j])));
+        const float ub = __fadd_ru(__fmaf_ru(__int2float_rn(vm), um, __ldg(dmax + (nb >> 5))), eta);
+        if (ub >= thr) {
+          float y[32];
 #pragma unroll
-        for (int j = 1; j < 32; j++) mx = fmaxf(mx, y[j]);
-        if (!have || mx > bv) {
-          // first column of the chunk that attains the maximum (greedy_sample keeps the first strict max)
-          int idx = 31;
+          for (int j = 0; j < 32; j += 4) {
+            if (nb + j < N) {  // N % 8 == 0: groups of four are entirely inside or outside
+              const float4 p4 = __ldg(reinterpret_cast<const float4*>(pb + nb + j));
+              const int4 c4 = __ldg(reinterpret_cast<const int4*>(c127 + nb + j));
+              y[j] = dequant1(static_cast<int>(v[j]) + c4.x, um, p4.x);
+              y[j + 1] = dequant1(static_cast<int>(v[j + 1]) + c4.y, um, p4.y);
+              y[j + 2] = dequant1(static_cast<int>(v[j + 2]) + c4.z, um, p4.z);
+              y[j + 3] = dequant1(static_cast<int>(v[j + 3]) + c4.w, um, p4.w);
+            } else {
+              y[j] = y[j + 1] = y[j + 2] = y[j + 3] = -__int_as_float(0x7f800000);
+            }
+          }
+          float mx = y[0];
 #pragma unroll
-          for (int j = 30; j >= 0; j--) idx = (y[j] == mx) ? j : idx;
-          bv = mx;
-          bi = static_cast<uint32_t>(nb + idx);
-          have = true;
+          for (int j = 1; j < 32; j++) mx = fmaxf(mx, y[j]);
+          if (!have || mx > bv) {
+            // first column of the chunk that attains the maximum (greedy_sample keeps the first strict max)
+            int idx = 31;
+#pragma unroll
+            for (int j = 30; j >= 0; j--) idx = (y[j] == mx) ? j : idx;
+            bv = mx;
+            bi = static_cast<uint32_t>(nb + idx);
+            have = true;
+            thr = fmaxf(thr, mx);
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-      const int row = m * kBM + q * 32 + lane;
       if (row < M && have) {
         // `best` only grows: a stale read can only cause a redundant atomic, never a missed one
         const unsigned long long key = pack_best_out(bv, bi);
-        if (key > __ldcg(best + row)) atomicMax(best + row, key);
+        if (key > seen) atomicMax(best + row, key);
       }
     }
   }
@@ -209,8 +235,9 @@ size_t out_smem_bytes(int KB) { return static_cast<size_t>(KB) * kOutBN * kBK + 
 
 }  // namespace
 
-int launch_gemm_out_argmax(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const float* pb, float um, int M, int N,
-                           int K, unsigned long long* best, int num_sms, cudaStream_t stream) {
+int launch_gemm_out_argmax(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const float* pb, const int32_t* c127,
+                           const float* dmax, float um, float eta, int M, int N, int K, unsigned long long* best,
+                           int num_sms, cudaStream_t stream) {
   const int KB = K / kBK;
   const long tiles = static_cast<long>((M + kBM - 1) / kBM) * ((N + kOutBN - 1) / kOutBN);
   const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
@@ -219,11 +246,11 @@ int launch_gemm_out_argmax(const CUtensorMap& tma_a, const CUtensorMap& tma_b, c
   if (KB == 2) {
     auto kern = out_argmax_kernel<2>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    kern<<<grid, kOutThreads, smem, stream>>>(tma_a, tma_b, pb, um, M, N, best);
+    kern<<<grid, kOutThreads, smem, stream>>>(tma_a, tma_b, pb, c127, dmax, um, eta, M, N, best);
   } else if (KB == 4) {
     auto kern = out_argmax_kernel<4>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    kern<<<grid, kOutThreads, smem, stream>>>(tma_a, tma_b, pb, um, M, N, best);
+    kern<<<grid, kOutThreads, smem, stream>>>(tma_a, tma_b, pb, c127, dmax, um, eta, M, N, best);
   } else {
     return 1;
   }

@@ -214,8 +214,9 @@ __global__ void finalize_step_kernel(unsigned long long* __restrict__ best, cons
 }
 
 __global__ void gather_rows_kernel(const int8_t* __restrict__ W, const float* __restrict__ pb,
-                                   const uint32_t* __restrict__ idx, int K, int8_t* __restrict__ W_sel,
-                                   float* __restrict__ pb_sel) {
+                                   const int32_t* __restrict__ c127, const uint32_t* __restrict__ idx, int K,
+                                   int8_t* __restrict__ W_sel, float* __restrict__ pb_sel,
+                                   int32_t* __restrict__ c127_sel) {
   const int i = blockIdx.x;
   const uint32_t src = idx[i];
   const uint4* s = reinterpret_cast<const uint4*>(W + static_cast<size_t>(src) * K);
@@ -223,7 +224,23 @@ __global__ void gather_rows_kernel(const int8_t* __restrict__ W, const float* __
   for (int t = threadIdx.x; t < K / 16; t += blockDim.x) d[t] = s[t];
   if (threadIdx.x == 0) {
     pb_sel[i] = pb[src];
+    if (c127_sel) c127_sel[i] = c127[src];
   }
+}
+
+// dmax[chunk] = max over the chunk's 32 columns of (c127[n] * um + pb[n]), rounded up to float: the
+// column-dependent part of the logit upper bound used by the fused output GEMM (gemm_out.cu).
+__global__ void out_bounds_kernel(const int32_t* __restrict__ c127, const float* __restrict__ pb, float um, int N,
+                                  float* __restrict__ dmax) {
+  const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (chunk * 32 >= N) return;
+  const int n = chunk * 32 + lane;
+  double d = -1.0e300;
+  if (n < N) d = static_cast<double>(c127[n]) * static_cast<double>(um) + static_cast<double>(pb[n]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
+  if (lane == 0) dmax[chunk] = __double2float_ru(d);
 }
 
 __device__ __forceinline__ unsigned long long pack_best_k(float v, uint32_t idx) {
@@ -301,10 +318,16 @@ void launch_finalize_step(unsigned long long* best, const uint32_t* shortlist, c
                                              sqrt_e, pos0, B, E, x, q);
 }
 
-void launch_gather_rows(const int8_t* W, const float* pb, const uint32_t* idx, int n_idx, int K, int8_t* W_sel,
-                        float* pb_sel, cudaStream_t stream) {
+void launch_gather_rows(const int8_t* W, const float* pb, const int32_t* c127, const uint32_t* idx, int n_idx, int K,
+                        int8_t* W_sel, float* pb_sel, int32_t* c127_sel, cudaStream_t stream) {
   if (n_idx == 0) return;
-  gather_rows_kernel<<<n_idx, 32, 0, stream>>>(W, pb, idx, K, W_sel, pb_sel);
+  gather_rows_kernel<<<n_idx, 32, 0, stream>>>(W, pb, c127, idx, K, W_sel, pb_sel, c127_sel);
+}
+
+void launch_out_bounds(const int32_t* c127, const float* pb, float um, int N, float* dmax, cudaStream_t stream) {
+  const int chunks = (N + 31) / 32;
+  if (chunks == 0) return;
+  out_bounds_kernel<<<(chunks + 7) / 8, 256, 0, stream>>>(c127, pb, um, N, dmax);
 }
 
 void launch_argmax_rows(const float* logits, int rows, int cols, unsigned long long* best, cudaStream_t stream) {

@@ -51,8 +51,12 @@ void launch_finalize_step(unsigned long long* best, const uint32_t* shortlist, c
                           cudaStream_t stream);
 
 // Shortlist: gather rows of the output weight and its prepared bias / shift terms.
-void launch_gather_rows(const int8_t* W, const float* pb, const uint32_t* idx, int n_idx, int K, int8_t* W_sel,
-                        float* pb_sel, cudaStream_t stream);
+// c127 / c127_sel (127 * column sums, used by the fused output GEMM's bound filter) may be null.
+void launch_gather_rows(const int8_t* W, const float* pb, const int32_t* c127, const uint32_t* idx, int n_idx, int K,
+                        int8_t* W_sel, float* pb_sel, int32_t* c127_sel, cudaStream_t stream);
+
+// dmax[ceil(N/32)]: per 32-column chunk, max_n(c127[n] * um + pb[n]) rounded up (see gemm_out.cu).
+void launch_out_bounds(const int32_t* c127, const float* pb, float um, int N, float* dmax, cudaStream_t stream);
 
 // Row-wise first-max over f32 logits (used when logits are materialised for parity taps).
 void launch_argmax_rows(const float* logits, int rows, int cols, unsigned long long* best, cudaStream_t stream);
