@@ -7,8 +7,8 @@
 // resident in shared memory for a whole run of row tiles -- it is the larger operand, so this halves
 // the L2 -> SM traffic -- while the u8 activation tiles (A, 128 rows x 128-byte k-blocks) stream
 // through a TMA/mbarrier ring; accumulators are double-buffered in TMEM (2 x 256 columns) so the MMAs
-// of tile i+1 overlap the epilogue of tile i.  Eight epilogue warps (TMEM lane quadrant x column half)
-// reduce their 128 columns to a first-maximum per row and publish (value, lowest index) with a
+// of tile i+1 overlap the epilogue of tile i.  Sixteen epilogue warps (TMEM lane quadrant x column
+// quarter) reduce their 64 columns to a first-maximum per row and publish (value, lowest index) with a
 // filtered 64-bit atomicMax.
 //
 // Epilogue arithmetic.  The exact logit is y = fl(fl(float(v) * um) + pb[n]) with v the SHIFTED
@@ -31,7 +31,7 @@ namespace {
 
 constexpr int kOutBN = 256;
 constexpr int kOutStages = 6;
-constexpr int kOutThreads = 384;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 epilogue
+constexpr int kOutThreads = 640;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-19 epilogue
 
 __device__ __forceinline__ unsigned long long pack_best_out(float v, uint32_t idx) {
   if (v == 0.0f) v = 0.0f;  // canonicalise -0 so equal values compare equal
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kOutThreads, 1)
     mbar_init(b_empty, 1);
     for (int i = 0; i < 2; i++) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&tmem_empty[i], 16);
     }
     fence_barrier_init();
   }
@@ -152,72 +152,107 @@ __global__ void __launch_bounds__(kOutThreads, 1)
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: thread <-> TMEM lane <-> output row; warps split the 256 columns in halves =====
+    // ===== epilogue: thread <-> TMEM lane <-> output row.  Sixteen warps: TMEM lane quadrant (warp % 4)
+    // x column quarter (64 columns = two 32-column chunks).  Both chunks are pulled into registers and the
+    // TMEM buffer is handed back to the MMA warp at once; bounds and (rarely) exact logits follow. =====
     const int e = warp - 4;
     const int q = warp & 3;
-    const int half = e >> 2;
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int quarter = e >> 2;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + quarter * 64;
+    const float ninf = -__int_as_float(0x7f800000);
+    const int nch = (N + 31) >> 5;
+    // prefetched per-tile inputs of the bound filter
+    unsigned long long seen_next = 0ull;
+    float dm0_next = ninf, dm1_next = ninf;
+    auto prefetch = [&](int t) {
+      const int n = t / m_tiles, m = t % m_tiles;
+      const int row = m * kBM + q * 32 + lane;
+      const int ch = (n * kOutBN + quarter * 64) >> 5;
+      seen_next = row < M ? __ldcg(best + row) : ~0ull;
+      dm0_next = ch < nch ? __ldg(dmax + ch) : ninf;
+      dm1_next = ch + 1 < nch ? __ldg(dmax + ch + 1) : ninf;
+    };
+    // exact logits of one 32-column chunk held in v[]; returns the chunk maximum and its first column
+    auto exact_chunk = [&](const uint32_t (&v)[32], int nb, float& mx, int& idx) {
+      float y[32];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (nb + j < N) {  // N % 8 == 0: groups of four are entirely inside or outside
+          const float4 p4 = __ldg(reinterpret_cast<const float4*>(pb + nb + j));
+          const int4 c4 = __ldg(reinterpret_cast<const int4*>(c127 + nb + j));
+          y[j] = dequant1(static_cast<int>(v[j]) + c4.x, um, p4.x);
+          y[j + 1] = dequant1(static_cast<int>(v[j + 1]) + c4.y, um, p4.y);
+          y[j + 2] = dequant1(static_cast<int>(v[j + 2]) + c4.z, um, p4.z);
+          y[j + 3] = dequant1(static_cast<int>(v[j + 3]) + c4.w, um, p4.w);
+        } else {
+          y[j] = y[j + 1] = y[j + 2] = y[j + 3] = ninf;
+        }
+      }
+      float t8[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) t8[j] = fmaxf(fmaxf(y[4 * j], y[4 * j + 1]), fmaxf(y[4 * j + 2], y[4 * j + 3]));
+      mx = fmaxf(fmaxf(fmaxf(t8[0], t8[1]), fmaxf(t8[2], t8[3])), fmaxf(fmaxf(t8[4], t8[5]), fmaxf(t8[6], t8[7])));
+      // first column of the chunk that attains the maximum (greedy_sample keeps the first strict max)
+      idx = 31;
+#pragma unroll
+      for (int j = 30; j >= 0; j--) idx = (y[j] == mx) ? j : idx;
+    };
+    auto int_max32 = [](const uint32_t (&v)[32]) {
+      int vt[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        vt[j] = max(max(static_cast<int>(v[4 * j]), static_cast<int>(v[4 * j + 1])),
+                    max(static_cast<int>(v[4 * j + 2]), static_cast<int>(v[4 * j + 3])));
+      return max(max(max(vt[0], vt[1]), max(vt[2], vt[3])), max(max(vt[4], vt[5]), max(vt[6], vt[7])));
+    };
+    if (t_begin < t_end) prefetch(t_begin);
     uint32_t i = 0;
     for (int t = t_begin; t < t_end; t++, i++) {
       const int n = t / m_tiles, m = t % m_tiles;
       const uint32_t buf = i & 1;
+      const unsigned long long seen = seen_next;
+      const float dm0 = dm0_next, dm1 = dm1_next;
+      if (t + 1 < t_end) prefetch(t + 1);
+      const int nb0 = n * kOutBN + quarter * 64;
+      const int row = m * kBM + q * 32 + lane;
       mbar_wait(&tmem_full[buf], (i >> 1) & 1);
       tc_fence_after();
-      const int n0 = n * kOutBN + half * 128;
-      const int row = m * kBM + q * 32 + lane;
+      uint32_t v0[32], v1[32];
+      tmem_ld32_nowait(lane_addr + buf * kOutBN, v0);
+      tmem_ld32_nowait(lane_addr + buf * kOutBN + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);  // accumulators are in registers: release the buffer
+
       // the row's best so far, from any CTA (monotone: a stale value only weakens the filter)
-      const unsigned long long seen = row < M ? __ldcg(best + row) : ~0ull;
-      float thr = -__int_as_float(0x7f800000);
+      float thr = ninf;
       if (seen != 0ull) {
         const uint32_t key = static_cast<uint32_t>(seen >> 32);
         thr = __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
       }
+      const float ub0 = nb0 < N ? __fadd_ru(__fmaf_ru(__int2float_rn(int_max32(v0)), um, dm0), eta) : ninf;
+      const float ub1 = nb0 + 32 < N ? __fadd_ru(__fmaf_ru(__int2float_rn(int_max32(v1)), um, dm1), eta) : ninf;
       float bv = 0.0f;
       uint32_t bi = 0;
       bool have = false;
-#pragma unroll 1
-      for (int c = 0; c < 4; c++) {
-        const int nb = n0 + c * 32;
-        if (nb >= N) break;
-        uint32_t v[32];
-        tmem_ld32(lane_addr + buf * kOutBN + half * 128 + c * 32, v);
-        int vm = static_cast<int>(v[0]);
-#pragma unroll
-        for (int j = 1; j < 32; j += 2) vm = max(vm, max(static_cast<int>(v[j]), static_cast<int>(v[j + 1 < 32 ? j + 1 : j])));
-        const float ub = __fadd_ru(__fmaf_ru(__int2float_rn(vm), um, __ldg(dmax + (nb >> 5))), eta);
-        if (ub >= thr) {
-          float y[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (nb + j < N) {  // N % 8 == 0: groups of four are entirely inside or outside
-              const float4 p4 = __ldg(reinterpret_cast<const float4*>(pb + nb + j));
-              const int4 c4 = __ldg(reinterpret_cast<const int4*>(c127 + nb + j));
-              y[j] = dequant1(static_cast<int>(v[j]) + c4.x, um, p4.x);
-              y[j + 1] = dequant1(static_cast<int>(v[j + 1]) + c4.y, um, p4.y);
-              y[j + 2] = dequant1(static_cast<int>(v[j + 2]) + c4.z, um, p4.z);
-              y[j + 3] = dequant1(static_cast<int>(v[j + 3]) + c4.w, um, p4.w);
-            } else {
-              y[j] = y[j + 1] = y[j + 2] = y[j + 3] = -__int_as_float(0x7f800000);
-            }
-          }
-          float mx = y[0];
-#pragma unroll
-          for (int j = 1; j < 32; j++) mx = fmaxf(mx, y[j]);
-          if (!have || mx > bv) {
-            // first column of the chunk that attains the maximum (greedy_sample keeps the first strict max)
-            int idx = 31;
-#pragma unroll
-            for (int j = 30; j >= 0; j--) idx = (y[j] == mx) ? j : idx;
-            bv = mx;
-            bi = static_cast<uint32_t>(nb + idx);
-            have = true;
-            thr = fmaxf(thr, mx);
-          }
+      if (__any_sync(0xffffffffu, ub0 >= thr && nb0 < N)) {
+        float mx;
+        int idx;
+        exact_chunk(v0, nb0, mx, idx);
+        if (nb0 < N && ub0 >= thr) {
+          bv = mx, bi = static_cast<uint32_t>(nb0 + idx), have = true;
+          thr = fmaxf(thr, mx);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (__any_sync(0xffffffffu, ub1 >= thr && nb0 + 32 < N)) {
+        float mx;
+        int idx;
+        exact_chunk(v1, nb0 + 32, mx, idx);
+        if (nb0 + 32 < N && ub1 >= thr && (!have || mx > bv)) {
+          bv = mx, bi = static_cast<uint32_t>(nb0 + 32 + idx), have = true;
+        }
+      }
       if (row < M && have) {
         // `best` only grows: a stale read can only cause a redundant atomic, never a missed one
         const unsigned long long key = pack_best_out(bv, bi);
