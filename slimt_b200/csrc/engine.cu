@@ -288,6 +288,7 @@ int Model::load(Context* c, const void* bin, size_t bytes, int enc_layers, int d
     host_prepare_bias(q, bias, w.aq, w.bq, K, N, pb.data());
     if (upload(q, static_cast<size_t>(K) * N, reinterpret_cast<void**>(&w.w))) return 1;
     if (upload(pb.data(), 4ul * N, reinterpret_cast<void**>(&w.pb))) return 1;
+    if (ctx->make_map(&w.map128, w.w, N, K, 128)) return 1;
     return 0;
   };
   auto ln = [&](const std::string& prefix, DevLN& l) -> int {
@@ -775,6 +776,11 @@ int model_forward(Model& m, ForwardArgs& a) {
     }
     Wout = Ws, pb_out = pbs, c127_out = cs, dmax_out = dms;
   }
+  CUtensorMap map_xq[2], map_zq[2], map_caq;  // u8 activation operands of the row-tile kernels, box {128 B, 32 rows}
+  for (int i = 0; i < 2; i++) {
+    if (c.make_map(&map_xq[i], xq[i], B, E, kRowTile) || c.make_map(&map_zq[i], zq[i], B, E, kRowTile)) return 1;
+  }
+  if (c.make_map(&map_caq, caq, B, E, kRowTile)) return 1;
   CUtensorMap map_oq, map_wout;
   if (c.make_map(&map_oq, oq, B, E, kBM) || c.make_map(&map_wout, Wout, Nout, E, 256)) return 1;
   float* d_logits = a.logits ? c.take<float>(static_cast<size_t>(B) * Nout) : nullptr;
@@ -798,31 +804,26 @@ int model_forward(Model& m, ForwardArgs& a) {
   int host_done = 0;
   for (int step = 0; step < max_steps; step++) {
     const float* in_f = xd;
-    int8_t* const* in_q = xq;
     for (int l = 0; l < Ld; l++) {
       const DecLayerW& L = m.dec[l];
       const bool last = (l + 1 == Ld);
-      {  // SSRU projections (Modules.cc:218-219)
-        GemmCall g(&c, "dec_gemm_ssru_f32", B, E, E, EPI_F32, 2);
-        GemmProblem* pf = g.add(in_q[0], L.rnn_wf);
-        GemmProblem* pw = g.add(in_q[1], L.rnn_w);
-        if (!pf || !pw) return 1;
-        pf->out = fb, pw->out = wxb;
-        pf->ldo = pw->ldo = E;
-        if (g.launch()) return 1;
-      }
-      {
-        QuantOuts q = qouts();
-        qadd(q, hq, L.ctx.q.aq);
-        LaunchScope ls(c, "dec_ssru_ln", 0, 25.0 * B * E);
-        launch_ssru_ln(fb, wxb, state[l], in_f, L.rnn_ln.scale, L.rnn_ln.bias, 1e-6f, B, E, hb, q, s);
-      }
-      {
-        GemmCall g(&c, "dec_gemm_q_f32", B, E, E, EPI_F32);
-        GemmProblem* p = g.add(hq, L.ctx.q);
-        if (!p) return 1;
-        p->out = qd, p->ldo = E;
-        if (g.launch()) return 1;
+      {  // SSRU cell + query projection in one row-tile kernel (Modules.cc:190-235, 291)
+        DecSsruArgs k{};
+        k.map_xf = l == 0 ? map_xq[0] : map_zq[0];
+        k.map_xw = l == 0 ? map_xq[1] : map_zq[1];
+        k.map_wf = L.rnn_wf.map128, k.map_w = L.rnn_w.map128, k.map_wq = L.ctx.q.map128;
+        k.pb_f = L.rnn_wf.pb, k.pb_w = L.rnn_w.pb, k.pb_q = L.ctx.q.pb;
+        k.um_f = L.rnn_wf.um, k.um_w = L.rnn_w.um, k.um_q = L.ctx.q.um;
+        k.aq_q = L.ctx.q.aq;
+        k.x = in_f, k.state = state[l];
+        k.ln_scale = L.rnn_ln.scale, k.ln_bias = L.rnn_ln.bias, k.eps = 1e-6f;
+        k.h_out = hb, k.q_out = qd, k.M = B;
+        const double Bd = B, Ed = E;
+        LaunchScope ls(c, "dec_ssru_q_fused", 2.0 * Bd * 3.0 * Ed * Ed, 3.0 * Ed * Ed + Bd * Ed * (2.0 + 4.0 * 5.0));
+        if (launch_dec_ssru(k, E, s)) {
+          set_error("fused SSRU kernel: unsupported embedding size " + std::to_string(E));
+          return 1;
+        }
       }
       {
         QuantOuts q = qouts();
@@ -831,40 +832,36 @@ int model_forward(Model& m, ForwardArgs& a) {
         launch_cross_attention(mapKc[l], mapVc[l], qd, d_lengths, B, T, H, dh, c.num_sms, nullptr, q,
                                last ? d_align : nullptr, s);
       }
-      {
-        GemmCall g(&c, "dec_gemm_wo_res_ln", B, E, E, EPI_RES_LN);
-        GemmProblem* p = g.add(caq, L.ctx.o);
-        if (!p) return 1;
-        p->residual = hb, p->ln_scale = L.ctx.ln.scale, p->ln_bias = L.ctx.ln.bias;
-        p->out = yb;
-        padd(p, yq, L.ffn.w1.aq);
-        if (g.launch()) return 1;
-      }
-      {
-        GemmCall g(&c, "dec_gemm_ffn1_relu_quant", B, F, E, EPI_QUANT);
-        GemmProblem* p = g.add(yq, L.ffn.w1);
-        if (!p) return 1;
-        p->relu = 1;
-        padd(p, fq, L.ffn.w2.aq);
-        if (g.launch()) return 1;
-      }
-      {
-        GemmCall g(&c, "dec_gemm_ffn2_res_ln", B, E, F, EPI_RES_LN);
-        GemmProblem* p = g.add(fq, L.ffn.w2);
-        if (!p) return 1;
-        p->residual = yb, p->ln_scale = L.ffn.ln.scale, p->ln_bias = L.ffn.ln.bias;
+      {  // Wo + residual + LN, FFN1 + ReLU, FFN2 + residual + LN in one row-tile kernel (Modules.cc:308-316, 251-257)
+        DecFfnArgs k{};
+        k.map_ca = map_caq;
+        k.map_wo = L.ctx.o.map128, k.map_w1 = L.ffn.w1.map128, k.map_w2 = L.ffn.w2.map128;
+        k.pb_o = L.ctx.o.pb, k.pb_1 = L.ffn.w1.pb, k.pb_2 = L.ffn.w2.pb;
+        k.um_o = L.ctx.o.um, k.um_1 = L.ffn.w1.um, k.um_2 = L.ffn.w2.um;
+        k.aq_1 = L.ffn.w1.aq, k.aq_2 = L.ffn.w2.aq;
+        k.h = hb;
+        k.ln1_scale = L.ctx.ln.scale, k.ln1_bias = L.ctx.ln.bias;
+        k.ln2_scale = L.ffn.ln.scale, k.ln2_bias = L.ffn.ln.bias, k.eps = 1e-6f;
         if (last) {
-          p->out = nullptr;
-          padd(p, oq, m.out.aq);
-          if (!a.logits) p->qout_signed = 1;  // the fused argmax GEMM takes the signed qa (gemm_out.cu)
+          k.z_out = nullptr;
+          k.zq[0] = reinterpret_cast<uint8_t*>(oq), k.zaq[0] = m.out.aq, k.n_zq = 1;
+          k.zq_signed = a.logits ? 0 : 1;  // the fused argmax GEMM takes the signed qa (gemm_out.cu)
         } else {
-          p->out = zb[l & 1];
-          padd(p, zq[0], m.dec[l + 1].rnn_wf.aq), padd(p, zq[1], m.dec[l + 1].rnn_w.aq);
+          k.z_out = zb[l & 1];
+          k.zq[0] = reinterpret_cast<uint8_t*>(zq[0]), k.zaq[0] = m.dec[l + 1].rnn_wf.aq;
+          k.zq[1] = reinterpret_cast<uint8_t*>(zq[1]), k.zaq[1] = m.dec[l + 1].rnn_w.aq;
+          k.n_zq = 2;
         }
-        if (g.launch()) return 1;
+        k.M = B;
+        const double Bd = B, Ed = E, Fd = F;
+        LaunchScope ls(c, "dec_wo_ffn_fused", 2.0 * Bd * (Ed * Ed + 2.0 * Ed * Fd),
+                       Ed * Ed + 2.0 * Ed * Fd + Bd * Ed * (1.0 + 4.0 + (last ? 1.0 : 6.0)));
+        if (launch_dec_ffn(k, E, F, s)) {
+          set_error("fused FFN kernel: unsupported sizes E=" + std::to_string(E) + " F=" + std::to_string(F));
+          return 1;
+        }
       }
       in_f = zb[l & 1];
-      in_q = zq;
     }
     // output projection (+ shortlist) and greedy choice (Transformer.cc:176-182, 279-339)
     if (d_logits) {

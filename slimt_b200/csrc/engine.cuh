@@ -11,6 +11,7 @@
 #include <tuple>
 #include <vector>
 
+#include "fused_rows.cuh"
 #include "gemm_i8.cuh"
 #include "kernels.cuh"
 
@@ -96,6 +97,7 @@ struct DevWeight {
   int K = 0, N = 0;
   float aq = 0, bq = 0, um = 0;
   int8_t* w = nullptr;      // [N][K]
+  CUtensorMap map128;       // TMA view of w with box {128 B, 128 rows}: the A operand of the row-tile kernels
   float* pb = nullptr;      // [N]
   // output layer only: inputs of the fused argmax GEMM's bound filter (gemm_out.cu)
   int32_t* c127 = nullptr;  // [N] 127 * colsum

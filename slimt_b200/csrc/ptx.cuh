@@ -121,6 +121,16 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 16 consecutive columns, no wait.
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // registers -> TMEM (same shape).
@@ -152,9 +162,18 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// Named barrier among a subset of the CTA's warps (id 1..15; `threads` must be a multiple of 32).
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // Instruction descriptor for kind::i8: D=s32, A=s8, B=s8, both K-major, M x N.
 //   [4,6) c_format=2 (S32)  [7,10) a_format=1 (INT8)  [10,13) b_format=1 (INT8)
 //   [15] a_major=0  [16] b_major=0  [17,23) N>>3  [24,29) M>>4
+// Weights as the A operand (s8, M = 128 output features) and u8 activations as B (N = rows of the tile).
+__host__ __device__ constexpr uint32_t make_idesc_i8_wa(uint32_t M, uint32_t N) {
+  return (2u << 4) | (1u << 7) | (0u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t make_idesc_i8(uint32_t M, uint32_t N) {
   return (2u << 4) | (0u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
