@@ -14,9 +14,9 @@ constexpr int kR = kRowTile;          // rows per CTA tile == UMMA N
 constexpr int kWTile = 128 * 128;     // one weight tile: 128 features x 128-byte k-block
 constexpr int kOpK = kR * 128;        // one k-block of an activation operand: 32 rows x 128 bytes
 constexpr int kSlots = 8;             // TMEM ring slots (32 columns each) for the FFN1 feature blocks
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = 128 + kEpiThreads;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 epilogue
+constexpr int kThreads = 128 + kEpiThreads;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-19 epilogue
 constexpr uint32_t kIdesc = make_idesc_i8_wa(128, kR);
 
 // ---- shared-memory plan -----------------------------------------------------------------------------
@@ -208,41 +208,51 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ffn_kernel(const __grid_const
       // ===== epilogue warps: TMEM lane = output feature, TMEM column = row of the tile
       const int ew = warp - 4;
       const int q = warp & 3;          // TMEM lane quadrant of this warp
-      const int rh = ew >> 2;          // which 16 rows of the tile
-      const int et = threadIdx.x - 128;  // 0..255
+      const int rq = ew >> 2;          // which 8 rows of the tile
+      const int et = threadIdx.x - 128;  // 0..511
       const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+      // LayerNorm apply phases: thread = (feature, contiguous block of rows)
+      constexpr int kParts = kEpiThreads / E;
+      constexpr int kRowsPer = kR / kParts;
+      const int nf = et % E;
+      const int nr0 = (et / E) * kRowsPer;
 
       // ---- epilogue 0: x = (Wo ca + bo) + h  -> xs
-      mbar_wait(g0_done, tph);
-      tc_fence_after();
+      {
+        float res[EM][8];
 #pragma unroll
-      for (int mb = 0; mb < EM; mb++) {
-        uint32_t v[16];
-        tmem_ld16_nowait(tmem_acc + lane_sel + mb * kR + rh * 16, v);
-        const int f = mb * 128 + q * 32 + lane;
-        const float pb = a.pb_o[f];
-        float res[16];
+        for (int mb = 0; mb < EM; mb++) {
 #pragma unroll
-        for (int r = 0; r < 16; r++) {
-          const int grow = row0 + rh * 16 + r;
-          res[r] = grow < a.M ? a.h[static_cast<size_t>(grow) * E + f] : 0.0f;
+          for (int r = 0; r < 8; r++) {
+            const int grow = row0 + rq * 8 + r;
+            res[mb][r] = grow < a.M ? a.h[static_cast<size_t>(grow) * E + mb * 128 + q * 32 + lane] : 0.0f;
+          }
         }
-        tmem_ld_wait();
+        mbar_wait(g0_done, tph);
+        tc_fence_after();
 #pragma unroll
-        for (int r = 0; r < 16; r++)
-          xs[(rh * 16 + r) * XS + f] = __fadd_rn(dequant1(static_cast<int>(v[r]), a.um_o, pb), res[r]);
+        for (int mb = 0; mb < EM; mb++) {
+          uint32_t v[8];
+          tmem_ld8_nowait(tmem_acc + lane_sel + mb * kR + rq * 8, v);
+          const int f = mb * 128 + q * 32 + lane;
+          const float pb = a.pb_o[f];
+          tmem_ld_wait();
+#pragma unroll
+          for (int r = 0; r < 8; r++)
+            xs[(rq * 8 + r) * XS + f] = __fadd_rn(dequant1(static_cast<int>(v[r]), a.um_o, pb), res[mb][r]);
+        }
       }
       named_bar_sync(1, kEpiThreads);
       if (ew == 0) ln_stats<E>(xs, stats, a.eps, lane);
       named_bar_sync(1, kEpiThreads);
       // y = LN1(x): keep it in xs (residual of the FFN block) and emit the u8 operand of W1
-      for (int f = et; f < E; f += kEpiThreads) {
-        const float g = a.ln1_scale[f], b = a.ln1_bias[f];
+      {
+        const float g = a.ln1_scale[nf], b = a.ln1_bias[nf];
 #pragma unroll 4
-        for (int r = 0; r < kR; r++) {
-          const float y = ln_apply(xs[r * XS + f], stats[r], stats[32 + r], g, b);
-          xs[r * XS + f] = y;
-          opnd_y[opnd_off(r, f)] = quant_byte(y, a.aq_1, false);
+        for (int r = nr0; r < nr0 + kRowsPer; r++) {
+          const float y = ln_apply(xs[r * XS + nf], stats[r], stats[32 + r], g, b);
+          xs[r * XS + nf] = y;
+          opnd_y[opnd_off(r, nf)] = quant_byte(y, a.aq_1, false);
         }
       }
       fence_proxy_async();
@@ -254,8 +264,8 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ffn_kernel(const __grid_const
         const uint32_t s = blocks_done % kSlots, ph = (blocks_done / kSlots) & 1;
         mbar_wait(&slot_full[s], ph);
         tc_fence_after();
-        uint32_t v[16];
-        tmem_ld16_nowait(tmem_ring + lane_sel + s * kR + rh * 16, v);
+        uint32_t v[8];
+        tmem_ld8_nowait(tmem_ring + lane_sel + s * kR + rq * 8, v);
         const float pb = a.pb_1[mb * 128 + q * 32 + lane];
         tmem_ld_wait();
         tc_fence_before();
@@ -264,10 +274,10 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ffn_kernel(const __grid_const
         uint8_t* dst = opnd_f + mb * kOpK;
         const int kk = q * 32 + lane;
 #pragma unroll
-        for (int r = 0; r < 16; r++) {
+        for (int r = 0; r < 8; r++) {
           float y = dequant1(static_cast<int>(v[r]), a.um_1, pb);
           y = y > 0.0f ? y : 0.0f;  // std::max<float>(0, a), TensorOps.cc:163
-          dst[opnd_off(rh * 16 + r, kk)] = quant_byte(y, a.aq_2, false);
+          dst[opnd_off(rq * 8 + r, kk)] = quant_byte(y, a.aq_2, false);
         }
         fence_proxy_async();
         __syncwarp();
@@ -279,14 +289,14 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ffn_kernel(const __grid_const
       tc_fence_after();
 #pragma unroll
       for (int mb = 0; mb < EM; mb++) {
-        uint32_t v[16];
-        tmem_ld16_nowait(tmem_acc + lane_sel + mb * kR + rh * 16, v);
+        uint32_t v[8];
+        tmem_ld8_nowait(tmem_acc + lane_sel + mb * kR + rq * 8, v);
         const int f = mb * 128 + q * 32 + lane;
         const float pb = a.pb_2[f];
         tmem_ld_wait();
 #pragma unroll
-        for (int r = 0; r < 16; r++) {
-          float* p = xs + (rh * 16 + r) * XS + f;
+        for (int r = 0; r < 8; r++) {
+          float* p = xs + (rq * 8 + r) * XS + f;
           *p = __fadd_rn(dequant1(static_cast<int>(v[r]), a.um_2, pb), *p);
         }
       }
@@ -294,14 +304,14 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ffn_kernel(const __grid_const
       named_bar_sync(1, kEpiThreads);
       if (ew == 0) ln_stats<E>(xs, stats, a.eps, lane);
       named_bar_sync(1, kEpiThreads);
-      for (int f = et; f < E; f += kEpiThreads) {
-        const float g = a.ln2_scale[f], b = a.ln2_bias[f];
+      {
+        const float g = a.ln2_scale[nf], b = a.ln2_bias[nf];
 #pragma unroll 4
-        for (int r = 0; r < kR; r++) {
+        for (int r = nr0; r < nr0 + kRowsPer; r++) {
           const int grow = row0 + r;
           if (grow >= a.M) break;
-          const float z = ln_apply(xs[r * XS + f], stats[r], stats[32 + r], g, b);
-          const size_t o = static_cast<size_t>(grow) * E + f;
+          const float z = ln_apply(xs[r * XS + nf], stats[r], stats[32 + r], g, b);
+          const size_t o = static_cast<size_t>(grow) * E + nf;
           if (a.z_out) a.z_out[o] = z;
           for (int k = 0; k < a.n_zq; k++) a.zq[k][o] = quant_byte(z, a.zaq[k], (a.zq_signed >> k) & 1);
         }
@@ -423,47 +433,59 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
     } else if (warp >= 4) {
       const int ew = warp - 4;
       const int q = warp & 3;
-      const int rh = ew >> 2;
+      const int rq = ew >> 2;
       const int et = threadIdx.x - 128;
       const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+      constexpr int kParts = kEpiThreads / E;
+      constexpr int kRowsPer = kR / kParts;
+      const int nf = et % E;
+      const int nr0 = (et / E) * kRowsPer;
 
       // ---- highway + relu + residual (slimt/Modules.cc:218-232, TensorOps.cc:662-682) -> xs
-      mbar_wait(g0_done, tph);
-      tc_fence_after();
-#pragma unroll 1
-      for (int mb = 0; mb < EM; mb++) {
-        uint32_t vf[16], vw[16];
-        tmem_ld16_nowait(tmem_f + lane_sel + mb * kR + rh * 16, vf);
-        tmem_ld16_nowait(tmem_w + lane_sel + mb * kR + rh * 16, vw);
-        const int f = mb * 128 + q * 32 + lane;
-        const float pbf = a.pb_f[f], pbw = a.pb_w[f];
-        tmem_ld_wait();
+      {
+        float st[EM][8], xv[EM][8];  // previous cell state and layer input of this thread's (rows, features)
 #pragma unroll
-        for (int r = 0; r < 16; r++) {
-          const int grow = row0 + rh * 16 + r;
-          float t = 0.0f;
-          if (grow < a.M) {
-            const size_t o = static_cast<size_t>(grow) * E + f;
+        for (int mb = 0; mb < EM; mb++) {
+#pragma unroll
+          for (int r = 0; r < 8; r++) {
+            const int grow = row0 + rq * 8 + r;
+            const size_t o = static_cast<size_t>(grow < a.M ? grow : 0) * E + mb * 128 + q * 32 + lane;
+            st[mb][r] = a.state[o];
+            xv[mb][r] = a.x[o];
+          }
+        }
+        mbar_wait(g0_done, tph);
+        tc_fence_after();
+#pragma unroll
+        for (int mb = 0; mb < EM; mb++) {
+          uint32_t vf[8], vw[8];
+          tmem_ld8_nowait(tmem_f + lane_sel + mb * kR + rq * 8, vf);
+          tmem_ld8_nowait(tmem_w + lane_sel + mb * kR + rq * 8, vw);
+          const int f = mb * 128 + q * 32 + lane;
+          const float pbf = a.pb_f[f], pbw = a.pb_w[f];
+          tmem_ld_wait();
+#pragma unroll
+          for (int r = 0; r < 8; r++) {
+            const int grow = row0 + rq * 8 + r;
             const float sg = sigmoid_ref_tab(dequant1(static_cast<int>(vf[r]), a.um_f, pbf), exp_tab);
             const float wx = dequant1(static_cast<int>(vw[r]), a.um_w, pbw);
-            const float c = __fadd_rn(__fmul_rn(sg, a.state[o]), __fmul_rn(__fsub_rn(1.0f, sg), wx));
-            a.state[o] = c;
-            t = __fadd_rn(a.x[o], c > 0.0f ? c : 0.0f);
+            const float c = __fadd_rn(__fmul_rn(sg, st[mb][r]), __fmul_rn(__fsub_rn(1.0f, sg), wx));
+            if (grow < a.M) a.state[static_cast<size_t>(grow) * E + f] = c;
+            xs[(rq * 8 + r) * XS + f] = __fadd_rn(xv[mb][r], c > 0.0f ? c : 0.0f);
           }
-          xs[(rh * 16 + r) * XS + f] = t;
         }
       }
       named_bar_sync(1, kEpiThreads);
       if (ew == 0) ln_stats<E>(xs, stats, a.eps, lane);
       named_bar_sync(1, kEpiThreads);
-      for (int f = et; f < E; f += kEpiThreads) {
-        const float g = a.ln_scale[f], b = a.ln_bias[f];
+      {
+        const float g = a.ln_scale[nf], b = a.ln_bias[nf];
 #pragma unroll 4
-        for (int r = 0; r < kR; r++) {
-          const float y = ln_apply(xs[r * XS + f], stats[r], stats[32 + r], g, b);
-          opnd_h[opnd_off(r, f)] = quant_byte(y, a.aq_q, false);
+        for (int r = nr0; r < nr0 + kRowsPer; r++) {
+          const float y = ln_apply(xs[r * XS + nf], stats[r], stats[32 + r], g, b);
+          opnd_h[opnd_off(r, nf)] = quant_byte(y, a.aq_q, false);
           const int grow = row0 + r;
-          if (grow < a.M) a.h_out[static_cast<size_t>(grow) * E + f] = y;
+          if (grow < a.M) a.h_out[static_cast<size_t>(grow) * E + nf] = y;
         }
       }
       fence_proxy_async();
@@ -475,14 +497,14 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
       tc_fence_after();
 #pragma unroll
       for (int mb = 0; mb < EM; mb++) {
-        uint32_t v[16];
-        tmem_ld16_nowait(tmem_q + lane_sel + mb * kR + rh * 16, v);
+        uint32_t v[8];
+        tmem_ld8_nowait(tmem_q + lane_sel + mb * kR + rq * 8, v);
         const int f = mb * 128 + q * 32 + lane;
         const float pb = a.pb_q[f];
         tmem_ld_wait();
 #pragma unroll
-        for (int r = 0; r < 16; r++) {
-          const int grow = row0 + rh * 16 + r;
+        for (int r = 0; r < 8; r++) {
+          const int grow = row0 + rq * 8 + r;
           if (grow < a.M) a.q_out[static_cast<size_t>(grow) * E + f] = dequant1(static_cast<int>(v[r]), a.um_q, pb);
         }
       }
