@@ -260,25 +260,36 @@ class Model:
         _check(lib().slimt_b200_model_forward(self.h, C.byref(io)), "slimt_b200_model_forward")
         return int(io.steps), int(io.target_tokens)
 
+    def translate_flat(self, tokens: np.ndarray, offsets: np.ndarray, max_words: int, limit_factor: float = 1.5,
+                       shortlist_bin: Optional[bytes] = None, out_tokens: Optional[np.ndarray] = None,
+                       out_offsets: Optional[np.ndarray] = None):
+        """slimt_b200_translate on caller-owned host buffers: ragged sentences in (tokens, offsets), ragged targets
+        out (out_tokens, out_offsets).  This is the C-ABI call a host integration makes; nothing is repacked."""
+        n = len(offsets) - 1
+        if out_offsets is None:
+            out_offsets = np.zeros(n + 1, dtype=np.uint64)
+        if out_tokens is None:
+            lens = np.diff(offsets.astype(np.int64))
+            max_len = int(lens.max()) if n else 0
+            out_tokens = np.zeros(max(1, n * (int(limit_factor * max_len) + 1)), dtype=np.uint32)
+        slbuf = None
+        if shortlist_bin is not None:
+            slbuf = shortlist_bin if isinstance(shortlist_bin, C.Array) else (C.c_char * len(shortlist_bin)).from_buffer_copy(shortlist_bin)
+        io = TranslateIO(_ptr(tokens), _ptr(offsets), n, max_words, limit_factor,
+                         C.cast(slbuf, C.c_void_p) if slbuf is not None else None,
+                         0 if slbuf is None else len(slbuf), _ptr(out_tokens), len(out_tokens),
+                         _ptr(out_offsets), 0, 0, 0.0, 0, 0, 0)
+        _check(lib().slimt_b200_translate(self.h, C.byref(io)), "slimt_b200_translate")
+        stats = {"target_tokens": int(io.target_tokens), "batches": int(io.batches), "device_ms": io.device_ms,
+                 "kernel_launches": int(io.kernel_launches), "h2d_bytes": int(io.h2d_bytes),
+                 "d2h_bytes": int(io.d2h_bytes)}
+        return out_tokens, out_offsets, stats
+
     def translate(self, sentences, max_words: int, limit_factor: float = 1.5, shortlist_bin: Optional[bytes] = None):
         """exhaust() over one request: Batcher + shortlist + forward per batch, host buffers in and out."""
         offsets = np.zeros(len(sentences) + 1, dtype=np.uint64)
         offsets[1:] = np.cumsum([len(s) for s in sentences])
         tokens = np.concatenate([np.asarray(s, dtype=np.uint32) for s in sentences]) if sentences else np.zeros(0, np.uint32)
-        max_len = max((len(s) for s in sentences), default=0)
-        cap = int(len(sentences) * (int(limit_factor * max_len) + 1))
-        out_tokens = np.zeros(max(cap, 1), dtype=np.uint32)
-        out_offsets = np.zeros(len(sentences) + 1, dtype=np.uint64)
-        slbuf = None
-        if shortlist_bin is not None:
-            slbuf = (C.c_char * len(shortlist_bin)).from_buffer_copy(shortlist_bin)
-        io = TranslateIO(_ptr(tokens), _ptr(offsets), len(sentences), max_words, limit_factor,
-                         C.cast(slbuf, C.c_void_p) if slbuf is not None else None,
-                         0 if shortlist_bin is None else len(shortlist_bin), _ptr(out_tokens), len(out_tokens),
-                         _ptr(out_offsets), 0, 0, 0.0, 0, 0, 0)
-        _check(lib().slimt_b200_translate(self.h, C.byref(io)), "slimt_b200_translate")
+        out_tokens, out_offsets, stats = self.translate_flat(tokens, offsets, max_words, limit_factor, shortlist_bin)
         outs = [out_tokens[int(out_offsets[i]):int(out_offsets[i + 1])].copy() for i in range(len(sentences))]
-        stats = {"target_tokens": int(io.target_tokens), "batches": int(io.batches), "device_ms": io.device_ms,
-                 "kernel_launches": int(io.kernel_launches), "h2d_bytes": int(io.h2d_bytes),
-                 "d2h_bytes": int(io.d2h_bytes)}
         return outs, stats

@@ -162,6 +162,22 @@ int slimt_b200_model_forward(slimt_b200_model* model, slimt_b200_forward_io* io)
   return rc;
 }
 
+namespace {
+struct LazyShortlist {
+  const sb::ShortlistGenerator* gen;
+  const std::vector<uint32_t>* words;
+  size_t vocab;
+  std::vector<uint32_t> out;
+};
+int lazy_shortlist_cb(void* user, const uint32_t** words, size_t* n) {
+  auto* l = static_cast<LazyShortlist*>(user);
+  l->out = l->gen->generate(l->words->data(), l->words->size(), l->vocab);
+  *words = l->out.data();
+  *n = l->out.size();
+  return 0;
+}
+}  // namespace
+
 int slimt_b200_translate(slimt_b200_model* model, slimt_b200_translate_io* io) {
   sb::Model& m = model->m;
   sb::Context& c = *m.ctx;
@@ -193,14 +209,15 @@ int slimt_b200_translate(slimt_b200_model* model, slimt_b200_translate_io* io) {
       lengths[r] = static_cast<uint32_t>(len);
       words.insert(words.end(), io->tokens + io->offsets[s], io->tokens + io->offsets[s + 1]);
     }
-    std::vector<uint32_t> sl;
-    if (use_sl) sl = gen.generate(words.data(), words.size(), m.V);
+    // Model::decode builds the candidate set before its first step (Model.cc:116-120); here the host does it
+    // while the GPU runs the encoder (the callback fires once the encoder kernels are queued)
+    LazyShortlist lazy{&gen, &words, static_cast<size_t>(m.V), {}};
     const size_t max_steps = static_cast<size_t>(io->limit_factor * static_cast<float>(width));
     std::vector<uint32_t> steps(std::max<size_t>(1, max_steps) * B);
     sb::ForwardArgs a;
     a.tokens = tokens.data(), a.lengths = lengths.data(), a.B = B, a.T = width;
     a.limit_factor = io->limit_factor;
-    a.shortlist = use_sl ? sl.data() : nullptr, a.n_shortlist = sl.size();
+    if (use_sl) a.shortlist_cb = lazy_shortlist_cb, a.shortlist_user = &lazy;
     a.step_tokens = steps.data();
     if (sb::model_forward(m, a)) {
       cudaEventDestroy(e0), cudaEventDestroy(e1);
@@ -209,6 +226,7 @@ int slimt_b200_translate(slimt_b200_model* model, slimt_b200_translate_io* io) {
     // record() (Model.cc:127-137): keep tokens up to and including the first EOS
     for (size_t r = 0; r < B; r++) {
       std::vector<uint32_t>& t = targets[batch[r]];
+      t.reserve(a.steps);
       for (size_t st = 0; st < a.steps; st++) {
         const uint32_t w = steps[st * B + r];
         t.push_back(w);

@@ -76,6 +76,8 @@ int Context::init(int dev) {
     return 1;
   }
   encode_tiled = reinterpret_cast<decltype(encode_tiled)>(fn);
+  SB_CUDA(cudaMallocHost(&done_slots, 8 * sizeof(int)));
+  for (auto& e : done_events) SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return 0;
 }
 
@@ -83,6 +85,9 @@ void Context::destroy() {
   cudaSetDevice(device);
   if (arena) cudaFree(arena);
   if (flush_buf) cudaFree(flush_buf);
+  if (done_slots) cudaFreeHost(done_slots);
+  for (auto& e : done_events)
+    if (e) cudaEventDestroy(e);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   if (stream) cudaStreamDestroy(stream);
@@ -564,9 +569,10 @@ int model_forward(Model& m, ForwardArgs& a) {
     src_tokens = 0;
     for (int b = 0; b < B; b++) src_tokens += std::min<uint32_t>(a.lengths[b], T);
   }
-  const bool use_sl = a.shortlist != nullptr && a.n_shortlist > 0;
-  const int Nout = use_sl ? static_cast<int>(a.n_shortlist) : m.V;
-  if (use_sl && a.n_shortlist % 8 != 0) {
+  const bool lazy_sl = a.shortlist == nullptr && a.shortlist_cb != nullptr && !a.device_io;
+  const bool use_sl = lazy_sl || (a.shortlist != nullptr && a.n_shortlist > 0);
+  int Nout = use_sl && !lazy_sl ? static_cast<int>(a.n_shortlist) : m.V;  // lazy: upper bound until the callback ran
+  if (use_sl && !lazy_sl && a.n_shortlist % 8 != 0) {
     set_error("shortlist size must be a multiple of 8");
     return 1;
   }
@@ -746,6 +752,18 @@ int model_forward(Model& m, ForwardArgs& a) {
       d_forced = t;
     }
   }
+  if (lazy_sl) {
+    // the encoder and the cross K/V projections are already queued: build the candidate set meanwhile
+    const uint32_t* words = nullptr;
+    size_t n = 0;
+    if (a.shortlist_cb(a.shortlist_user, &words, &n)) return 1;
+    if (n == 0 || n % 8 != 0 || n > static_cast<size_t>(m.V)) {
+      set_error("shortlist size must be a positive multiple of 8 no larger than the vocabulary");
+      return 1;
+    }
+    a.shortlist = words, a.n_shortlist = n;
+    Nout = static_cast<int>(n);
+  }
   const uint32_t* d_sl = nullptr;
   const int8_t* Wout = m.out.w;
   const float* pb_out = m.out.pb;
@@ -899,14 +917,26 @@ int model_forward(Model& m, ForwardArgs& a) {
                            m.pos, B, E, xd, q, s);
     }
     executed = step + 1;
-    // Model.cc:161: the loop stops once every sentence has produced EOS.  Poll the device counter
-    // every few steps (one 4-byte read) rather than synchronising each step.
-    if ((step & 3) == 3 || step + 1 == max_steps) {
-      SB_CUDA(cudaMemcpyAsync(&host_done, counters, 4, cudaMemcpyDeviceToHost, s));
-      SB_CUDA(cudaStreamSynchronize(s));
+    // Model.cc:161: the loop stops once every sentence has produced EOS.  The done-counter of each step is
+    // copied to a pinned slot behind an event; the host looks at the slot from kLag steps ago, so the
+    // stream always holds a few queued steps and is never drained (extra steps only produce discarded tokens).
+    {
+      constexpr int kSlots = 8, kLag = 4;
+      const int slot = step % kSlots;
+      SB_CUDA(cudaMemcpyAsync(&c.done_slots[slot], counters, 4, cudaMemcpyDeviceToHost, s));
+      SB_CUDA(cudaEventRecord(c.done_events[slot], s));
       c.d2h_bytes += 4;
-      if (host_done >= B) break;
+      if (step >= kLag) {
+        const int old = (step - kLag) % kSlots;
+        SB_CUDA(cudaEventSynchronize(c.done_events[old]));
+        host_done = c.done_slots[old];
+        if (host_done >= B) break;
+      }
     }
+  }
+  if (executed > 0 && host_done < B) {
+    SB_CUDA(cudaStreamSynchronize(s));
+    host_done = c.done_slots[(executed - 1) % 8];
   }
 
   // ---- results

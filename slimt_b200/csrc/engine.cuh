@@ -46,6 +46,9 @@ struct Context {
   size_t flush_bytes = 0;
   uint64_t launches = 0;
   uint64_t h2d_bytes = 0, d2h_bytes = 0;
+  // early-exit polling of the decode loop: pinned slots + events, so the host never drains the stream
+  int* done_slots = nullptr;  // pinned host [kPollSlots]
+  cudaEvent_t done_events[8] = {};
   // optional per-kernel device timing (CUDA events around every launch on `stream`)
   struct ProfRec {
     const char* tag;
@@ -152,6 +155,10 @@ struct ForwardArgs {
   float limit_factor = 1.5f;
   const uint32_t* shortlist = nullptr;
   size_t n_shortlist = 0;
+  // Alternative to `shortlist` (host-buffer mode only): called once, after the encoder has been enqueued,
+  // so that ShortlistGenerator::generate runs on the host while the GPU works.  Returns nonzero on failure.
+  int (*shortlist_cb)(void* user, const uint32_t** words, size_t* n) = nullptr;
+  void* shortlist_user = nullptr;
   const uint32_t* forced = nullptr;
   bool device_io = false;
   uint32_t* step_tokens = nullptr;

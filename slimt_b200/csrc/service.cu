@@ -43,27 +43,33 @@ int ShortlistGenerator::load(const void* data, size_t bytes) {
 }
 
 std::vector<uint32_t> ShortlistGenerator::generate(const uint32_t* words, size_t n, size_t vocab) const {
-  std::vector<bool> source_table(vocab, false), target_table(vocab, false);
-  for (uint32_t i = 0; i < frequent && i < vocab; ++i) target_table[i] = true;
-  for (size_t t = 0; t < n; t++) {
+  // byte tables instead of the reference's std::vector<bool>: same marks, no bit twiddling on the hot loop
+  std::vector<uint8_t> source_table(word_to_offset_size, 0), target_table(vocab, 0);
+  size_t ones = 0;
+  for (uint32_t i = 0; i < frequent && i < vocab; ++i) target_table[i] = 1, ones++;
+  // a large batch's union saturates the vocabulary early: once every id is marked nothing can change
+  for (size_t t = 0; t < n && ones < vocab; t++) {
     const uint32_t word = words[t];
     if (word + 1 >= word_to_offset_size || source_table[word]) continue;
-    for (uint64_t j = word_to_offset[word]; j < word_to_offset[word + 1]; j++) target_table[shortlist[j]] = true;
-    source_table[word] = true;
+    source_table[word] = 1;
+    const uint32_t* p = shortlist + word_to_offset[word];
+    const uint32_t* e = shortlist + word_to_offset[word + 1];
+    for (; p != e; ++p) {
+      ones += 1 - target_table[*p];
+      target_table[*p] = 1;
+    }
   }
-  size_t ones = 0;
-  for (size_t i = 0; i < vocab; i++) ones += target_table[i] ? 1 : 0;
   // pad to a multiple of eight with the next unused ids >= frequent (Shortlist.cc:158-164)
   for (size_t i = frequent; i < vocab && ones % 8 != 0; i++) {
     if (!target_table[i]) {
-      target_table[i] = true;
+      target_table[i] = 1;
       ones++;
     }
   }
-  std::vector<uint32_t> indices;
-  indices.reserve(ones);
+  std::vector<uint32_t> indices(ones);
+  size_t k = 0;
   for (uint32_t i = 0; i < vocab; i++)
-    if (target_table[i]) indices.push_back(i);
+    if (target_table[i]) indices[k++] = i;
   return indices;
 }
 
