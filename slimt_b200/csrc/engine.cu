@@ -629,6 +629,9 @@ int model_forward(Model& m, ForwardArgs& a) {
     if (c.make_map_f32(&mapKc[l], Kc[l], R, E, box_rows) || c.make_map_f32(&mapVc[l], Vc[l], R, E, box_rows)) return 1;
   }
 
+  CUtensorMap map_attn_q;  // u8 [R][E], box {128 B, 128 rows}: operand of the encoder's row-tile kernel
+  if (c.make_map(&map_attn_q, attn_q, R, E, 128)) return 1;
+
   // ---- embedding (Model.cc:195-197)
   {
     QuantOuts q = qouts();
@@ -657,6 +660,40 @@ int model_forward(Model& m, ForwardArgs& a) {
       qadd(q, attn_q, L.self.o.aq);
       LaunchScope ls(c, "enc_self_attention", 0, 13.0 * R * E);
       launch_self_attention(Qb, Kb, Vb, d_lengths, B, T, H, dh, nullptr, q, s);
+    }
+    if (E == 256 && F == 1536) {
+      // Wo + residual + LN, FFN1 + ReLU, FFN2 + residual + LN in one row-tile kernel, 128 rows per CTA
+      RowsFfnArgs k{};
+      k.map_a = map_attn_q;
+      k.map_wo = L.self.o.map128, k.map_w1 = L.ffn.w1.map128, k.map_w2 = L.ffn.w2.map128;
+      k.pb_o = L.self.o.pb, k.pb_1 = L.ffn.w1.pb, k.pb_2 = L.ffn.w2.pb;
+      k.um_o = L.self.o.um, k.um_1 = L.ffn.w1.um, k.um_2 = L.ffn.w2.um;
+      k.aq_1 = L.ffn.w1.aq, k.aq_2 = L.ffn.w2.aq;
+      k.res = x0, k.y_park = x1, k.z_out = x0;
+      k.ln1_scale = L.self.ln.scale, k.ln1_bias = L.self.ln.bias;
+      k.ln2_scale = L.ffn.ln.scale, k.ln2_bias = L.ffn.ln.bias, k.eps = 1e-6f;
+      if (i + 1 < Le) {
+        const EncLayerW& Nx = m.enc[i + 1];
+        k.zq[0] = reinterpret_cast<uint8_t*>(qa[0]), k.zaq[0] = Nx.self.q.aq;
+        k.zq[1] = reinterpret_cast<uint8_t*>(qa[1]), k.zaq[1] = Nx.self.k.aq;
+        k.zq[2] = reinterpret_cast<uint8_t*>(qa[2]), k.zaq[2] = Nx.self.v.aq;
+        k.n_zq = 3;
+      } else {
+        for (int l = 0; l < Ld; l++) {
+          k.zq[2 * l] = reinterpret_cast<uint8_t*>(qa[2 * l]), k.zaq[2 * l] = m.dec[l].ctx.k.aq;
+          k.zq[2 * l + 1] = reinterpret_cast<uint8_t*>(qa[2 * l + 1]), k.zaq[2 * l + 1] = m.dec[l].ctx.v.aq;
+        }
+        k.n_zq = 2 * Ld;
+      }
+      k.M = R;
+      const double Rd = R, Ed = E, Fd = F;
+      LaunchScope ls(c, "enc_wo_ffn_fused", 2.0 * Rd * (Ed * Ed + 2.0 * Ed * Fd),
+                     Ed * Ed + 2.0 * Ed * Fd + Rd * Ed * (1.0 + 4.0 + 8.0 + 4.0 + k.n_zq));
+      if (launch_rows_ffn(k, E, F, 128, s)) {
+        set_error("fused encoder FFN kernel launch failed");
+        return 1;
+      }
+      continue;
     }
     {
       GemmCall g(&c, "enc_gemm_wo_res_ln", R, E, E, EPI_RES_LN);
@@ -851,13 +888,13 @@ int model_forward(Model& m, ForwardArgs& a) {
                                last ? d_align : nullptr, s);
       }
       {  // Wo + residual + LN, FFN1 + ReLU, FFN2 + residual + LN in one row-tile kernel (Modules.cc:308-316, 251-257)
-        DecFfnArgs k{};
-        k.map_ca = map_caq;
+        RowsFfnArgs k{};
+        k.map_a = map_caq;
         k.map_wo = L.ctx.o.map128, k.map_w1 = L.ffn.w1.map128, k.map_w2 = L.ffn.w2.map128;
         k.pb_o = L.ctx.o.pb, k.pb_1 = L.ffn.w1.pb, k.pb_2 = L.ffn.w2.pb;
         k.um_o = L.ctx.o.um, k.um_1 = L.ffn.w1.um, k.um_2 = L.ffn.w2.um;
         k.aq_1 = L.ffn.w1.aq, k.aq_2 = L.ffn.w2.aq;
-        k.h = hb;
+        k.res = hb;
         k.ln1_scale = L.ctx.ln.scale, k.ln1_bias = L.ctx.ln.bias;
         k.ln2_scale = L.ffn.ln.scale, k.ln2_bias = L.ffn.ln.bias, k.eps = 1e-6f;
         if (last) {
@@ -874,7 +911,7 @@ int model_forward(Model& m, ForwardArgs& a) {
         const double Bd = B, Ed = E, Fd = F;
         LaunchScope ls(c, "dec_wo_ffn_fused", 2.0 * Bd * (Ed * Ed + 2.0 * Ed * Fd),
                        Ed * Ed + 2.0 * Ed * Fd + Bd * Ed * (1.0 + 4.0 + (last ? 1.0 : 6.0)));
-        if (launch_dec_ffn(k, E, F, s)) {
+        if (launch_rows_ffn(k, E, F, kRowTile, s)) {
           set_error("fused FFN kernel: unsupported sizes E=" + std::to_string(E) + " F=" + std::to_string(F));
           return 1;
         }

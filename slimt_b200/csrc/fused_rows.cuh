@@ -17,25 +17,26 @@ namespace sb {
 
 constexpr int kRowTile = 32;
 
-// Cross-attention output projection + residual + LayerNorm, then the feed-forward block with its own
-// residual + LayerNorm:  y = LN1(h + Wo ca + bo);  z = LN2(y + W2 relu(W1 y + b1) + b2).
-struct DecFfnArgs {
-  CUtensorMap map_ca;                  // u8 [M][E], box {128 B, 32 rows}: attention output quantised with Wo's a_quant
+// Attention output projection + residual + LayerNorm, then the feed-forward block with its own residual +
+// LayerNorm (encoder and decoder layers):  y = LN1(res + Wo a + bo);  z = LN2(y + W2 relu(W1 y + b1) + b2).
+struct RowsFfnArgs {
+  CUtensorMap map_a;                   // u8 [M][E], box {128 B, rows_per_tile}: attention output quantised with Wo's a_quant
   CUtensorMap map_wo, map_w1, map_w2;  // s8 weights [N][K], box {128 B, 128 rows}
   const float* pb_o;                   // prepared biases (Int8Shift::PrepareBias, precomputed at load)
   const float* pb_1;
   const float* pb_2;
   float um_o, um_1, um_2;              // 1 / (a_quant * b_quant)
   float aq_1, aq_2;                    // a_quant of W1 (quantises y) and W2 (quantises relu(W1 y + b1))
-  const float* h;                      // residual of the attention block, f32 [M][E]
+  const float* res;                    // residual of the attention block, f32 [M][E]
   const float* ln1_scale;
   const float* ln1_bias;
   const float* ln2_scale;
   const float* ln2_bias;
   float eps;
+  float* y_park;                       // f32 [M][E] scratch for y, required when rows_per_tile == 128
   float* z_out;                        // f32 [M][E] or null
-  uint8_t* zq[2];                      // quantised copies of z for the consumers (next layer's Wf / W, or the output layer)
-  float zaq[2];
+  uint8_t* zq[4];                      // quantised copies of z for the consumers (next layer's projections, output layer)
+  float zaq[4];
   int n_zq;
   int zq_signed;                       // bit k: zq[k] receives the signed value instead of u8 = q + 127
   int M;
@@ -62,7 +63,8 @@ struct DecSsruArgs {
 };
 
 // E = 256, F = 1536 (tiny) and E = 512, F = 2048 (base) are built.  Returns nonzero when unsupported.
-int launch_dec_ffn(const DecFfnArgs& a, int E, int F, cudaStream_t stream);
+// rows_per_tile: 32 (decoder step) or 128 (encoder; E = 256 only).
+int launch_rows_ffn(const RowsFfnArgs& a, int E, int F, int rows_per_tile, cudaStream_t stream);
 int launch_dec_ssru(const DecSsruArgs& a, int E, cudaStream_t stream);
 
 }  // namespace sb
