@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
           } else {
             xs[row * XS + nf] = y;
           }
-          dst[r * 128 + xn[r & 7]] = quant_byte(y, a.aq_1, false);
+          dst[r * 128 + xn[r & 7]] = static_cast<uint8_t>(quantize1(y, a.aq_1));
         }
       }
       fence_proxy_async();
@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
 #pragma unroll
         for (int r = 0; r < RPW; r++) {
           float y = dequant1(static_cast<int>(v[r]), a.um_1, pb);
-          y = y > 0.0f ? y : 0.0f;  // std::max<float>(0, a), TensorOps.cc:163
-          dst[r * 128 + xo[r & 7]] = quant_byte(y, a.aq_2, false);
+          y = fmaxf(y, 0.0f);  // std::max<float>(0, a), TensorOps.cc:163 (NaN -> 0 and -0 -> +0 either way)
+          dst[r * 128 + xo[r & 7]] = static_cast<uint8_t>(quantize1(y, a.aq_2));
         }
         fence_proxy_async();
         __syncwarp();
@@ -277,14 +277,27 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
       named_bar_sync(1, kEpiThreads);
       {
         const float g = a.ln2_scale[nf], b = a.ln2_bias[nf];
+        // consumers' quantised copies: pointers and multipliers in registers, sign handling decided once
+        uint8_t* zp[4];
+        float za[4];
+        int zsub[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          zp[k] = k < a.n_zq ? a.zq[k] + static_cast<size_t>(row0) * E + nf : nullptr;
+          za[k] = k < a.n_zq ? a.zaq[k] : 0.0f;
+          zsub[k] = ((a.zq_signed >> k) & 1) ? 127 : 0;
+        }
+        float* zo = a.z_out ? a.z_out + static_cast<size_t>(row0) * E + nf : nullptr;
+        const int rows_here = min(kRowsPer, a.M - row0 - nr0);
 #pragma unroll 4
-        for (int r = nr0; r < nr0 + kRowsPer; r++) {
-          const int grow = row0 + r;
-          if (grow >= a.M) break;
-          const float z = ln_apply(xs[r * XS + nf], stats[r], stats[R + r], g, b);
-          const size_t o = static_cast<size_t>(grow) * E + nf;
-          if (a.z_out) a.z_out[o] = z;
-          for (int k = 0; k < a.n_zq; k++) a.zq[k][o] = quant_byte(z, a.zaq[k], (a.zq_signed >> k) & 1);
+        for (int r = 0; r < rows_here; r++) {
+          const int row = nr0 + r;
+          const float z = ln_apply(xs[row * XS + nf], stats[row], stats[R + row], g, b);
+          const size_t o = static_cast<size_t>(row) * E;
+          if (zo) zo[o] = z;
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (zp[k]) zp[k][o] = static_cast<uint8_t>(quantize1(z, za[k]) - zsub[k]);
         }
       }
     }
