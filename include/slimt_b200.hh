@@ -1,0 +1,398 @@
+// slimt_b200.hh -- host-side C++ mirror of slimt's API surface for the hot path, over the C ABI in
+// slimt_b200.h.  Header only; link with libslimt_b200.so.  Same names, argument meaning and error
+// behaviour as the reference for the slice that sits on the path:
+//
+//   slimt::Tensor / Shape / Type            slimt/Tensor.hh:16-154   (row-major dense, owning or view)
+//   slimt::qmm::affine / affine_with_select / dot / prepare_weight_*   slimt/QMM.hh:48-63
+//   slimt::Input                            slimt/Input.hh:10-37     (padded batch of word ids)
+//   slimt::Model::forward -> Histories      slimt/Model.hh:31-83, Model.cc:187-204
+//   slimt::Config, slimt::Blocking, slimt::Async   slimt/Frontend.hh:21-78
+//
+// Everything above Model::forward in the reference works on text (TextProcessor, Vocabulary, Response,
+// Annotation, HTML): those stay the reference's own code and are out of scope here, so the services below
+// take and return word ids (slimt::Words), which is what the reference hands to Model::forward too
+// (Frontend.cc:30-60).  Not meant to be included together with the reference's own headers: inside the slimt
+// tree the same C ABI is bound by the provider file shown in INTEGRATION.md.
+//
+// Error convention: the reference asserts / aborts on shape violations (qmm/Gemmology.inl.cc:51,141,
+// Macros.hh:30-42) and throws std::runtime_error from its loaders (Io.cc:294-309); here every failure of the
+// C ABI is a std::runtime_error carrying slimt_b200_last_error().  There is no CPU fallback.
+#pragma once
+#include <condition_variable>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <future>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <utility>
+#include <vector>
+
+#include "slimt_b200.h"
+
+namespace slimt {
+
+using Word = uint32_t;
+using Words = std::vector<Word>;
+using Sentences = std::vector<Words>;
+template <class T>
+using Ptr = std::shared_ptr<T>;
+using Distribution = std::vector<float>;
+using Alignment = std::vector<Distribution>;
+struct View {
+  void *data = nullptr;
+  size_t size = 0;
+};
+struct Hypothesis {
+  Words target;
+  Alignment alignment;
+};
+using History = Ptr<Hypothesis>;
+using Histories = std::vector<History>;
+
+namespace detail {
+inline void check(int rc, const char *what) {
+  if (rc != 0) throw std::runtime_error(std::string(what) + ": " + slimt_b200_last_error());
+}
+// one context per device, created on first use and kept for the life of the process
+inline slimt_b200_ctx *context(int device = 0) {
+  static std::mutex mu;
+  static std::vector<slimt_b200_ctx *> ctxs;
+  std::lock_guard<std::mutex> lock(mu);
+  if (static_cast<size_t>(device) >= ctxs.size()) ctxs.resize(device + 1, nullptr);
+  if (ctxs[device] == nullptr) check(slimt_b200_ctx_create(device, &ctxs[device]), "slimt_b200_ctx_create");
+  return ctxs[device];
+}
+}  // namespace detail
+
+// ---------------------------------------------------------------- Tensor (slimt/Tensor.hh)
+enum class Type { i8, ig8, i32, u32, f32 };
+inline size_t size_in_bytes(Type t) { return (t == Type::i8 || t == Type::ig8) ? 1 : 4; }
+
+class Shape {
+ public:
+  Shape() = default;
+  Shape(std::initializer_list<uint64_t> dims) : dims_(dims) {}
+  explicit Shape(std::vector<uint64_t> dims) : dims_(std::move(dims)) {}
+  uint64_t dim(int64_t i) const { return dims_[i < 0 ? dims_.size() + i : i]; }  // negative = from the end
+  size_t size() const { return dims_.size(); }
+  size_t elements() const {
+    size_t n = 1;
+    for (uint64_t d : dims_) n *= d;
+    return n;
+  }
+  const std::vector<uint64_t> &dims() const { return dims_; }
+  void set_dim(int64_t i, uint64_t v) { dims_[i < 0 ? dims_.size() + i : i] = v; }
+
+ private:
+  std::vector<uint64_t> dims_;
+};
+
+class Tensor {
+ public:
+  Tensor() = default;
+  Tensor(Type type, Shape shape, std::string name = "") : type_(type), shape_(std::move(shape)), name_(std::move(name)) {
+    bytes_ = shape_.elements() * size_in_bytes(type_);
+    // 64-byte aligned like slimt::Aligned (Aligned.cc:45-52); ig8 weights carry their f32 multiplier after the bytes
+    size_t alloc = ((bytes_ + (type_ == Type::ig8 ? 4 : 0) + 63) / 64) * 64;
+    own_.reset(static_cast<char *>(std::aligned_alloc(64, alloc ? alloc : 64)), std::free);
+    data_ = own_.get();
+  }
+  // non-owning view (Tensor::load, Tensor.cc:87-93)
+  void load(View view, Type type, Shape shape, std::string name) {
+    own_.reset();
+    data_ = view.data, bytes_ = view.size, type_ = type, shape_ = std::move(shape), name_ = std::move(name);
+  }
+  template <class T>
+  T *data() { return static_cast<T *>(data_); }
+  template <class T>
+  const T *data() const { return static_cast<const T *>(data_); }
+  uint64_t dim(int64_t i) const { return shape_.dim(i); }
+  const Shape &shape() const { return shape_; }
+  Type type() const { return type_; }
+  size_t size() const { return shape_.elements(); }
+  const std::string &name() const { return name_; }
+  Tensor clone() const {
+    Tensor t(type_, shape_, name_);
+    std::memcpy(t.data_, data_, bytes_ + (type_ == Type::ig8 ? 4 : 0));
+    return t;
+  }
+
+ private:
+  Type type_ = Type::f32;
+  Shape shape_;
+  std::string name_;
+  std::shared_ptr<char> own_;
+  void *data_ = nullptr;
+  size_t bytes_ = 0;
+};
+
+// ---------------------------------------------------------------- qmm:: (slimt/QMM.hh:48-63)
+namespace qmm {
+namespace detail {
+inline Tensor run(const Tensor &x, const Tensor &W, const float *bias, float a_quant, float b_quant,
+                  const std::vector<uint32_t> *indices, const std::string &name) {
+  // x [..., K] f32; W prepared int8 of logical shape {K, N} (Io.cc:227-228) stored as B^T [N][K]
+  const size_t K = x.dim(-1), M = x.size() / K;
+  const size_t N = W.dim(-1);
+  if (W.dim(-2) != K) throw std::runtime_error("qmm: inner dimensions of x and W differ");
+  Shape out = x.shape();
+  out.set_dim(-1, indices ? indices->size() : N);
+  Tensor y(Type::f32, out, name);
+  ::slimt::detail::check(
+      slimt_b200_qmm_affine(::slimt::detail::context(), x.data<float>(), M, K, W.data<int8_t>(), N, bias, a_quant, b_quant,
+                            indices ? indices->data() : nullptr, indices ? indices->size() : 0, y.data<float>()),
+      "slimt_b200_qmm_affine");
+  return y;
+}
+}  // namespace detail
+
+inline Tensor affine(const Tensor &x, const Tensor &W, const Tensor &b, float a_quant, float b_quant,
+                     const std::string &name = "") {
+  return detail::run(x, W, b.data<float>(), a_quant, b_quant, nullptr, name);
+}
+inline Tensor affine_with_select(const Tensor &x, const Tensor &W, const Tensor &b, float a_quant, float b_quant,
+                                 const std::vector<uint32_t> &indices, const std::string &name = "") {
+  return detail::run(x, W, b.data<float>(), a_quant, b_quant, &indices, name);
+}
+inline Tensor dot(const Tensor &x, const Tensor &W, float a_quant, float b_quant, const std::string &name = "") {
+  return detail::run(x, W, nullptr, a_quant, b_quant, nullptr, name);
+}
+inline void prepare_weight_transposed(const float *weights, int8_t *prepared, float quantization_multiplier, size_t cols,
+                                      size_t rows) {
+  slimt_b200_qmm_prepare_weight_transposed(weights, prepared, quantization_multiplier, cols, rows);
+}
+inline void prepare_weight_quantized_transposed(const int8_t *input, int8_t *output, size_t rows, size_t cols) {
+  slimt_b200_qmm_prepare_weight_quantized_transposed(input, output, rows, cols);
+}
+}  // namespace qmm
+
+// ---------------------------------------------------------------- Input (slimt/Input.hh)
+class Input {
+ public:
+  Input(size_t batch_size, size_t sequence_length, uint32_t pad_id, float limit_factor)
+      : batch_(Type::u32, Shape({batch_size, sequence_length}), "batch"), pad_id_(pad_id), limit_factor_(limit_factor) {
+    std::fill(batch_.data<uint32_t>(), batch_.data<uint32_t>() + batch_.size(), pad_id);
+  }
+  void add(const std::vector<uint32_t> &words) {
+    const size_t T = batch_.dim(-1);
+    if (index_ >= batch_.dim(-2) || words.size() > T) throw std::runtime_error("Input::add: batch or sequence overflow");
+    std::memcpy(batch_.data<uint32_t>() + index_ * T, words.data(), 4 * words.size());
+    words_.insert(words_.end(), words.begin(), words.end());
+    lengths_.push_back(words.size());
+    ++index_;
+  }
+  void finalize() {}  // the additive mask (Input.cc:49-63) is implied by lengths() on the device
+  const Tensor &indices() const { return batch_; }
+  const std::vector<uint32_t> &words() const { return words_; }
+  const std::vector<size_t> &lengths() const { return lengths_; }
+  size_t index() const { return index_; }
+  float limit_factor() const { return limit_factor_; }
+
+ private:
+  std::vector<uint32_t> words_;
+  std::vector<size_t> lengths_;
+  Tensor batch_;
+  size_t index_ = 0;
+  uint32_t pad_id_ = 0;
+  float limit_factor_;
+};
+
+// ---------------------------------------------------------------- Model (slimt/Model.hh)
+template <class Field>
+struct Package {
+  Field model;      // marian binary v1 (model.intgemm.alphas.bin)
+  Field vocabulary; // unused on this path (word ids in, word ids out)
+  Field shortlist;  // lex.s2t.bin or empty
+};
+
+class Model {
+ public:
+  struct Config {  // Model.hh:33-51
+    size_t encoder_layers = 6;
+    size_t decoder_layers = 2;
+    size_t feed_forward_depth = 2;
+    size_t num_heads = 8;
+    std::string split_mode = "sentence";
+  };
+
+  Model(const Config &config, const Package<View> &package, int device = 0) : config_(config), device_(device) {
+    slimt_b200_model_config c{static_cast<int32_t>(config.encoder_layers), static_cast<int32_t>(config.decoder_layers),
+                              static_cast<int32_t>(config.feed_forward_depth), static_cast<int32_t>(config.num_heads)};
+    detail::check(slimt_b200_model_create(detail::context(device), package.model.data, package.model.size, &c, &model_),
+                  "slimt_b200_model_create");
+    int32_t e = 0, f = 0, v = 0;
+    slimt_b200_model_dims(model_, &e, &f, &v);
+    vocab_ = static_cast<size_t>(v);
+    if (package.shortlist.data != nullptr && package.shortlist.size > 0) {
+      shortlist_.assign(static_cast<const char *>(package.shortlist.data),
+                        static_cast<const char *>(package.shortlist.data) + package.shortlist.size);
+    }
+  }
+  ~Model() { slimt_b200_model_destroy(model_); }
+  Model(const Model &) = delete;
+  Model &operator=(const Model &) = delete;
+
+  // Model::forward (Model.cc:187-204): embedding -> encoder -> greedy decode with the per-batch shortlist.
+  Histories forward(const Input &input) const {
+    const size_t B = input.index(), T = input.indices().dim(-1);
+    std::vector<uint32_t> lengths(input.lengths().begin(), input.lengths().end());
+    std::vector<uint32_t> shortlist;
+    if (!shortlist_.empty()) {
+      shortlist.resize(vocab_ + 8);
+      size_t n = 0;
+      detail::check(slimt_b200_shortlist_generate(shortlist_.data(), shortlist_.size(), input.words().data(),
+                                                  input.words().size(), vocab_, shortlist.data(), shortlist.size(), &n),
+                    "slimt_b200_shortlist_generate");
+      shortlist.resize(n);
+    }
+    const size_t max_steps = static_cast<size_t>(input.limit_factor() * static_cast<float>(T));
+    std::vector<uint32_t> steps(std::max<size_t>(1, max_steps) * std::max<size_t>(1, B));
+    std::vector<float> align(steps.size() * T);
+    slimt_b200_forward_io io;
+    std::memset(&io, 0, sizeof(io));
+    io.tokens = input.indices().data<uint32_t>(), io.lengths = lengths.data(), io.batch = B, io.seq = T;
+    io.limit_factor = input.limit_factor();
+    io.shortlist = shortlist.empty() ? nullptr : shortlist.data(), io.n_shortlist = shortlist.size();
+    io.step_tokens = steps.data(), io.alignment = align.data();
+    {
+      std::lock_guard<std::mutex> lock(mu_);  // one stream and workspace per context: forward calls are serialised
+      detail::check(slimt_b200_model_forward(model_, &io), "slimt_b200_model_forward");
+    }
+    Histories histories;
+    for (size_t b = 0; b < B; b++) {  // record() + update_alignment (Model.cc:84-137)
+      auto h = std::make_shared<Hypothesis>();
+      for (size_t s = 0; s < io.steps; s++) {
+        const uint32_t w = steps[s * B + b];
+        h->target.push_back(w);
+        const float *row = align.data() + (s * B + b) * T;
+        h->alignment.emplace_back(row, row + lengths[b]);
+        if (w == 0u) break;  // eos id
+      }
+      histories.push_back(std::move(h));
+    }
+    return histories;
+  }
+  const Config &config() const { return config_; }
+  size_t vocabulary_size() const { return vocab_; }
+  int device() const { return device_; }
+  slimt_b200_model *handle() const { return model_; }
+  const std::vector<char> &shortlist_image() const { return shortlist_; }
+
+ private:
+  Config config_;
+  int device_ = 0;
+  slimt_b200_model *model_ = nullptr;
+  size_t vocab_ = 0;
+  std::vector<char> shortlist_;
+  mutable std::mutex mu_;
+};
+
+// ---------------------------------------------------------------- services (slimt/Frontend.hh)
+struct Config {
+  size_t max_words = 1024;
+  size_t cache_size = 1024;
+  size_t workers = 1;
+  float tgt_length_limit_factor = 1.5;
+  size_t wrap_length = 128;
+};
+
+// Blocking::translate (Frontend.cc:91-145 + exhaust() :42-60) on word ids: Batcher, per-batch shortlist,
+// Model::forward per batch, all inside one C-ABI call.
+class Blocking {
+ public:
+  explicit Blocking(const Config &config) : config_(config) {}
+  Sentences translate(const Ptr<Model> &model, const Sentences &sources) {
+    std::vector<uint32_t> tokens;
+    std::vector<uint64_t> offsets(1, 0);
+    size_t longest = 0;
+    for (const Words &s : sources) {
+      tokens.insert(tokens.end(), s.begin(), s.end());
+      offsets.push_back(tokens.size());
+      longest = std::max(longest, s.size());
+    }
+    const size_t per = static_cast<size_t>(config_.tgt_length_limit_factor * static_cast<float>(longest)) + 1;
+    std::vector<uint32_t> out(std::max<size_t>(1, per * sources.size()));
+    std::vector<uint64_t> out_offsets(sources.size() + 1, 0);
+    slimt_b200_translate_io io;
+    std::memset(&io, 0, sizeof(io));
+    io.tokens = tokens.data(), io.offsets = offsets.data(), io.n_sentences = sources.size();
+    io.max_words = config_.max_words, io.limit_factor = config_.tgt_length_limit_factor;
+    const std::vector<char> &sl = model->shortlist_image();
+    io.shortlist_bin = sl.empty() ? nullptr : sl.data(), io.shortlist_bytes = sl.size();
+    io.out_tokens = out.data(), io.out_capacity = out.size(), io.out_offsets = out_offsets.data();
+    detail::check(slimt_b200_translate(model->handle(), &io), "slimt_b200_translate");
+    Sentences targets(sources.size());
+    for (size_t i = 0; i < sources.size(); i++) targets[i].assign(out.begin() + out_offsets[i], out.begin() + out_offsets[i + 1]);
+    return targets;
+  }
+
+ private:
+  Config config_;
+};
+
+// Async (Frontend.cc:207-323): `workers` threads pull requests from one queue and answer through futures.
+// With one Model replica per GPU (models[i] lives on device i) this is the multi-GPU service: sentences are
+// independent, replicas share nothing, no collective is involved.
+class Async {
+ public:
+  Async(const Config &config, std::vector<Ptr<Model>> replicas) : config_(config), replicas_(std::move(replicas)) {
+    for (const Ptr<Model> &m : replicas_) workers_.emplace_back([this, m]() { work(m); });
+  }
+  ~Async() {
+    {
+      std::lock_guard<std::mutex> lock(mu_);
+      shutdown_ = true;
+    }
+    cv_.notify_all();
+    for (std::thread &t : workers_) t.join();
+  }
+  std::future<Sentences> translate(Sentences sources) {
+    Job job;
+    job.sources = std::move(sources);
+    std::future<Sentences> f = job.promise.get_future();
+    {
+      std::lock_guard<std::mutex> lock(mu_);
+      queue_.push_back(std::move(job));
+    }
+    cv_.notify_one();
+    return f;
+  }
+
+ private:
+  struct Job {
+    Sentences sources;
+    std::promise<Sentences> promise;
+  };
+  void work(const Ptr<Model> &model) {
+    Blocking service(config_);
+    for (;;) {
+      Job job;
+      {
+        std::unique_lock<std::mutex> lock(mu_);
+        cv_.wait(lock, [this]() { return shutdown_ || !queue_.empty(); });
+        if (queue_.empty()) return;
+        job = std::move(queue_.front());
+        queue_.pop_front();
+      }
+      try {
+        job.promise.set_value(service.translate(model, job.sources));
+      } catch (...) {
+        job.promise.set_exception(std::current_exception());
+      }
+    }
+  }
+  Config config_;
+  std::vector<Ptr<Model>> replicas_;
+  std::vector<std::thread> workers_;
+  std::deque<Job> queue_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  bool shutdown_ = false;
+};
+
+}  // namespace slimt

@@ -1,0 +1,89 @@
+// Exercises the C++ host layer (include/slimt_b200.hh) the way slimt's own callers use the reference:
+// qmm::affine on Tensors, Model::forward on an Input, Blocking::translate and Async::translate on word ids.
+// Usage: host_api_test <model.bin> <shortlist.bin|-> <sentences.u32> <out.bin>
+//   sentences.u32: u32 n, then per sentence u32 len + words.   out.bin: see write() calls below.
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <iterator>
+
+#include "slimt_b200.hh"
+
+static std::vector<char> slurp(const char *path) {
+  std::ifstream f(path, std::ios::binary);
+  return std::vector<char>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+static void put(std::ofstream &o, const void *p, size_t n) { o.write(static_cast<const char *>(p), n); }
+static void put_sentences(std::ofstream &o, const slimt::Sentences &s) {
+  uint32_t n = s.size();
+  put(o, &n, 4);
+  for (const auto &w : s) {
+    uint32_t len = w.size();
+    put(o, &len, 4);
+    put(o, w.data(), 4 * w.size());
+  }
+}
+
+int main(int argc, char **argv) {
+  if (argc < 5) return 2;
+  try {
+    std::vector<char> model_bin = slurp(argv[1]);
+    std::vector<char> sl_bin = std::string(argv[2]) == "-" ? std::vector<char>() : slurp(argv[2]);
+    std::vector<char> raw = slurp(argv[3]);
+    if (model_bin.empty() || raw.size() < 4) throw std::runtime_error("cannot read the model or the sentences file");
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(raw.data());
+    slimt::Sentences sources(*p++);
+    size_t longest = 0;
+    for (auto &s : sources) {
+      uint32_t len = *p++;
+      s.assign(p, p + len);
+      p += len;
+      longest = std::max<size_t>(longest, len);
+    }
+    std::ofstream out(argv[4], std::ios::binary);
+
+    // 1. qmm::affine on Tensors (QMM.hh:48): x [4,64] f32, W {64,16} ig8 as B^T [16][64], bias [1,16]
+    slimt::Tensor x(slimt::Type::f32, slimt::Shape({4, 64}), "x");
+    slimt::Tensor W(slimt::Type::ig8, slimt::Shape({64, 16}), "W");
+    slimt::Tensor b(slimt::Type::f32, slimt::Shape({1, 16}), "b");
+    for (size_t i = 0; i < x.size(); i++) x.data<float>()[i] = 0.01f * static_cast<float>(static_cast<int>(i % 97) - 48);
+    for (size_t i = 0; i < W.size(); i++) W.data<int8_t>()[i] = static_cast<int8_t>(static_cast<int>((i * 37) % 255) - 127);
+    for (size_t i = 0; i < b.size(); i++) b.data<float>()[i] = 0.1f * static_cast<float>(i);
+    slimt::Tensor y = slimt::qmm::affine(x, W, b, 127.0f / 0.5f, 127.0f / 2.0f, "y");
+    put(out, y.data<float>(), 4 * y.size());
+
+    // 2. Model::forward on one Input holding every sentence (Model.cc:187)
+    slimt::Package<slimt::View> package{{model_bin.data(), model_bin.size()}, {nullptr, 0}, {sl_bin.data(), sl_bin.size()}};
+    auto model = std::make_shared<slimt::Model>(slimt::Model::Config{}, package);
+    slimt::Input input(sources.size(), longest, 0, 1.5f);
+    for (const auto &s : sources) input.add(s);
+    input.finalize();
+    slimt::Histories histories = model->forward(input);
+    slimt::Sentences forward_targets;
+    for (const auto &h : histories) forward_targets.push_back(h->target);
+    put_sentences(out, forward_targets);
+    uint32_t n_align = histories.empty() ? 0 : histories[0]->alignment.size();
+    put(out, &n_align, 4);
+    for (uint32_t s = 0; s < n_align; s++) put(out, histories[0]->alignment[s].data(), 4 * histories[0]->alignment[s].size());
+
+    // 3. Blocking::translate (Frontend.cc:91) with small batches
+    slimt::Config config;
+    config.max_words = 96;
+    slimt::Blocking blocking(config);
+    put_sentences(out, blocking.translate(model, sources));
+
+    // 4. Async::translate (Frontend.cc:229) through one replica
+    {
+      slimt::Async async(config, {model});
+      std::future<slimt::Sentences> f1 = async.translate(sources);
+      std::future<slimt::Sentences> f2 = async.translate(slimt::Sentences(sources.begin(), sources.begin() + 1));
+      put_sentences(out, f1.get());
+      put_sentences(out, f2.get());
+    }
+    std::printf("host_api_test ok\n");
+    return 0;
+  } catch (const std::exception &e) {
+    std::fprintf(stderr, "host_api_test: %s\n", e.what());
+    return 1;
+  }
+}

@@ -1,0 +1,103 @@
+"""The C++ host layer (include/slimt_b200.hh): slimt's Tensor / qmm:: / Input / Model / Blocking / Async surface
+over the C ABI.  CPU: the header compiles, links against the library and fails loudly without a GPU.  GPU: its
+results equal the ctypes path (which the other GPU suites pin bit-exactly to the oracle)."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import sb_testutil as util
+from slimt_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "host_api_test")
+
+
+def _build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "slimt_b200", "csrc"), "host_test"])
+    assert os.path.exists(BIN)
+
+
+def _write_sentences(path, sents):
+    with open(path, "wb") as f:
+        f.write(struct.pack("<I", len(sents)))
+        for s in sents:
+            f.write(struct.pack("<I", len(s)) + np.asarray(s, dtype=np.uint32).tobytes())
+
+
+def _read_sentences(buf, pos):
+    n, = struct.unpack_from("<I", buf, pos)
+    pos += 4
+    out = []
+    for _ in range(n):
+        ln, = struct.unpack_from("<I", buf, pos)
+        pos += 4
+        out.append(np.frombuffer(buf, dtype=np.uint32, count=ln, offset=pos).tolist())
+        pos += 4 * ln
+    return out, pos
+
+
+def test_host_layer_builds_and_refuses_to_run_without_gpu(tiny_model, tmp_path):
+    _build()
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present; the refusal path is for CPU-only hosts")
+    except ImportError:
+        pass
+    sents = synth.make_sentences(3, (2, 6), seed=5)
+    _write_sentences(tmp_path / "s.u32", sents)
+    r = subprocess.run([BIN, tiny_model[0], "-", str(tmp_path / "s.u32"), str(tmp_path / "o.bin")], capture_output=True, text=True)
+    assert r.returncode == 1
+    assert "no CPU fallback" in r.stderr or "CUDA" in r.stderr
+
+
+@pytest.mark.gpu
+def test_host_layer_matches_ctypes_path(gpu_ctx, tiny_model, shortlist_assets, tmp_path):
+    from oracle import slimt_oracle as so
+    from slimt_b200 import capi
+    _build()
+    path, items = tiny_model
+    sl_path, (fr, offs, lists) = shortlist_assets
+    sents = synth.make_sentences(20, (2, 12), seed=91)
+    _write_sentences(tmp_path / "s.u32", sents)
+    subprocess.run([BIN, path, sl_path, str(tmp_path / "s.u32"), str(tmp_path / "o.bin")], check=True)
+    buf = open(tmp_path / "o.bin", "rb").read()
+
+    # 1. qmm::affine on the same deterministic operands
+    x = (0.01 * ((np.arange(4 * 64) % 97) - 48)).astype(np.float32).reshape(4, 64)
+    W = (((np.arange(64 * 16) * 37) % 255) - 127).astype(np.int8).reshape(16, 64)
+    b = (0.1 * np.arange(16)).astype(np.float32)
+    y_ref = so.affine(x, W, b, float(np.float32(127.0) / np.float32(0.5)), float(np.float32(127.0) / np.float32(2.0)))
+    y_ref = y_ref[0] if isinstance(y_ref, tuple) else y_ref
+    y = np.frombuffer(buf, dtype=np.float32, count=64).reshape(4, 16)
+    assert np.array_equal(y, y_ref)
+    pos = 256
+
+    # 2. Model::forward == oracle on the same single batch (shortlist = union over the batch)
+    fwd, pos = _read_sentences(buf, pos)
+    tokens, lengths = util.pad_batch(sents)
+    sl = so.shortlist_generate(np.concatenate(sents), fr, offs, lists, 32000)
+    ref = so.Oracle(items).forward(tokens, lengths, shortlist=sl, keep=True)
+    assert fwd == ref["sentences"]
+    n_align, = struct.unpack_from("<I", buf, pos)
+    pos += 4
+    assert n_align == len(ref["sentences"][0])
+    for s in range(n_align):
+        row = np.frombuffer(buf, dtype=np.float32, count=int(lengths[0]), offset=pos)
+        pos += 4 * int(lengths[0])
+        assert np.array_equal(row, ref["attn"][s][0, 0, 0, :lengths[0]])
+
+    # 3. Blocking::translate == the ctypes translate with the same max_words; 4. Async twice
+    m = capi.Model(gpu_ctx, open(path, "rb").read())
+    outs, _ = m.translate(sents, max_words=96, shortlist_bin=open(sl_path, "rb").read())
+    blocking, pos = _read_sentences(buf, pos)
+    assert blocking == [o.tolist() for o in outs]
+    a1, pos = _read_sentences(buf, pos)
+    a2, pos = _read_sentences(buf, pos)
+    assert a1 == blocking
+    one, _ = m.translate(sents[:1], max_words=96, shortlist_bin=open(sl_path, "rb").read())
+    assert a2 == [one[0].tolist()]
+    m.close()
