@@ -167,6 +167,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="bracket the timed steps with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -223,12 +225,18 @@ def main():
     sampler.start()
     launches0 = ctx.launches()
     step_ms, tokens_per_step = [], 0
+    if args.profiler_range:
+        import torch
+        torch.cuda.cudart().cudaProfilerStart()
     for _ in range(args.steps):
         ctx.flush_l2()
         ctx.timer_start()
         tokens_per_step = resident_pass()
         step_ms.append(ctx.timer_stop())
     launches = ctx.launches() - launches0
+    if args.profiler_range:
+        ctx.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     barrier()
     clocks = sampler.stop()
     total_ms = sum(step_ms)

@@ -67,9 +67,10 @@ def test_host_layer_matches_ctypes_path(gpu_ctx, tiny_model, shortlist_assets, t
     buf = open(tmp_path / "o.bin", "rb").read()
 
     # 1. qmm::affine on the same deterministic operands
-    x = (0.01 * ((np.arange(4 * 64) % 97) - 48)).astype(np.float32).reshape(4, 64)
+    # same float32 arithmetic as tests/cpp/host_api_test.cc (0.01f * float(i % 97 - 48), 0.1f * float(i))
+    x = (np.float32(0.01) * ((np.arange(4 * 64) % 97) - 48).astype(np.float32)).reshape(4, 64)
     W = (((np.arange(64 * 16) * 37) % 255) - 127).astype(np.int8).reshape(16, 64)
-    b = (0.1 * np.arange(16)).astype(np.float32)
+    b = np.float32(0.1) * np.arange(16).astype(np.float32)
     y_ref = so.affine(x, W, b, float(np.float32(127.0) / np.float32(0.5)), float(np.float32(127.0) / np.float32(2.0)))
     y_ref = y_ref[0] if isinstance(y_ref, tuple) else y_ref
     y = np.frombuffer(buf, dtype=np.float32, count=64).reshape(4, 16)

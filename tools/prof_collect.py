@@ -20,6 +20,7 @@ path = os.path.join(ROOT, "gpurun_out", f"{tag}_launches.csv")
 if os.path.exists(path):
     lines = [l for l in open(path) if l.startswith('"')]
     rows = list(csv.reader(lines))
+if os.path.exists(path) and rows:
     hdr = rows[0]
     ik, iv, im = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name")
     agg = {}

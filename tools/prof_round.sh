@@ -4,8 +4,8 @@
 set -x
 TAG=${1:-r1}
 BENCH="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
-# 3 warm-up passes x ~1224 launches are skipped; the 4th (timed) pass is listed
-ncu --metrics gpu__time_duration.sum --clock-control none -s 3700 -c 1300 --csv --log-file gpurun_out/${TAG}_launches.csv $BENCH > gpurun_out/${TAG}_launches.log 2>&1
+# only the timed pass is listed: bench.py brackets it with cudaProfilerStart/Stop
+ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 3000 --csv --log-file gpurun_out/${TAG}_launches.csv $BENCH --profiler-range > gpurun_out/${TAG}_launches.log 2>&1
 for spec in "cross_attention:100:1" "out_argmax:20:1" "rows_ffn_kernel:0:1" "rows_ffn_kernel:8:1" "dec_ssru_kernel:8:1" "self_attention:2:1" "gemm_i8_kernel:2:2"; do
   IFS=: read pat skip cnt <<< "$spec"
   ncu --set full --clock-control none --import-source on -k regex:$pat -s $skip -c $cnt -o gpurun_out/${TAG}_${pat}_s${skip} $BENCH > gpurun_out/${TAG}_${pat}_s${skip}.log 2>&1
