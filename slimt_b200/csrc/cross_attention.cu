@@ -30,7 +30,7 @@ __global__ void __launch_bounds__((H + 1) * 32, 3)
   constexpr int E = H * DH;
   constexpr int kSub = DH / 32;  // 128-byte column tiles per head
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   const uint32_t tile_bytes = static_cast<uint32_t>(box_rows) * 128u;
   const uint32_t chunk_bytes = tile_bytes * H * kSub;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * chunk_bytes);
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__((H + 1) * 32, 3)
     for (int c = 0; c < NC; c++) {
       if (c < nc) {
         const int j = c * 32 + lane;
-        sc[c] = (j < len) ? expf_glibc_tab(__fsub_rn(sc[c], mx), exp_tab) : 0.0f;
+        sc[c] = (j < len) ? expf_glibc_nonpos_tab(__fsub_rn(sc[c], mx), exp_tab) : 0.0f;
         // sum in key order (slimt/TensorOps.cc:296-314): exp of a masked key is +0 and adding it is exact
         __syncwarp();
         sp[lane] = sc[c];

@@ -855,6 +855,14 @@ int model_forward(Model& m, ForwardArgs& a) {
     launch_embed(nullptr, m.emb_q, m.inv_qm, m.sqrt_e, m.pos, B, 1, E, 0, 1, xd, q, s);
   }
 
+  // debugging aid: SLIMT_B200_TRACE=<file> records the phase stamps of the row-tile kernels of one decode step
+  const char* trace_path = getenv("SLIMT_B200_TRACE");
+  long long* trace_buf = nullptr;
+  const size_t trace_n = static_cast<size_t>(c.num_sms) * kTraceSlots;
+  if (trace_path) {
+    SB_CUDA(cudaMallocManaged(&trace_buf, 2 * trace_n * sizeof(long long)));
+    SB_CUDA(cudaMemsetAsync(trace_buf, 0, 2 * trace_n * sizeof(long long), s));
+  }
   int executed = 0;
   int host_done = 0;
   for (int step = 0; step < max_steps; step++) {
@@ -873,6 +881,7 @@ int model_forward(Model& m, ForwardArgs& a) {
         k.x = in_f, k.state = state[l];
         k.ln_scale = L.rnn_ln.scale, k.ln_bias = L.rnn_ln.bias, k.eps = 1e-6f;
         k.h_out = hb, k.q_out = qd, k.M = B;
+        if (trace_buf && step == 3 && l == 0) k.trace = trace_buf;
         const double Bd = B, Ed = E;
         LaunchScope ls(c, "dec_ssru_q_fused", 2.0 * Bd * 3.0 * Ed * Ed, 3.0 * Ed * Ed + Bd * Ed * (2.0 + 4.0 * 5.0));
         if (launch_dec_ssru(k, E, s)) {
@@ -908,6 +917,7 @@ int model_forward(Model& m, ForwardArgs& a) {
           k.n_zq = 2;
         }
         k.M = B;
+        if (trace_buf && step == 3 && l == 0) k.trace = trace_buf + trace_n;
         const double Bd = B, Ed = E, Fd = F;
         LaunchScope ls(c, "dec_wo_ffn_fused", 2.0 * Bd * (Ed * Ed + 2.0 * Ed * Fd),
                        Ed * Ed + 2.0 * Ed * Fd + Bd * Ed * (1.0 + 4.0 + (last ? 1.0 : 6.0)));
@@ -974,6 +984,22 @@ int model_forward(Model& m, ForwardArgs& a) {
   if (executed > 0 && host_done < B) {
     SB_CUDA(cudaStreamSynchronize(s));
     host_done = c.done_slots[(executed - 1) % 8];
+  }
+
+  if (trace_buf) {
+    SB_CUDA(cudaStreamSynchronize(s));
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int k = 0; k < 2; k++)
+        for (int cta = 0; cta < c.num_sms; cta++) {
+          const long long* t = trace_buf + k * trace_n + static_cast<size_t>(cta) * kTraceSlots;
+          if (t[0] == 0) continue;
+          fprintf(f, "%s %d", k == 0 ? "ssru" : "ffn", cta);
+          for (int i = 0; i < kTraceSlots; i++) fprintf(f, " %lld", t[i] ? t[i] - t[0] : -1);
+          fprintf(f, "\n");
+        }
+      fclose(f);
+    }
+    cudaFree(trace_buf);
   }
 
   // ---- results

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
   constexpr int EK = E / 128, EM = E / 128;
   constexpr int XS = E + 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* ring = smem + L::ring;
   uint8_t* opnd_xf = smem + L::opnd_xf;
   uint8_t* opnd_xw = smem + L::opnd_xw;
@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::tmem_slot);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) SB_TRACE(a, 0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.map_xf);
     tma_prefetch_desc(&a.map_xw);
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (threadIdx.x == 0) SB_TRACE(a, 1);
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_f = tmem;                    // gate pre-activations Wf x
   const uint32_t tmem_w = tmem + EM * kR;          // W x
@@ -108,16 +110,20 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
     } else if (warp == 1) {
       if (lane == 0) {
         mbar_wait(x_full, tph);
+        SB_TRACE(a, 2);
         for (int mb = 0; mb < EM; mb++)
           for (int kb = 0; kb < EK; kb++) cons.mma(tmem_f + mb * kR, opnd_xf + kb * kOpK, kb == 0);
         for (int mb = 0; mb < EM; mb++)
           for (int kb = 0; kb < EK; kb++) cons.mma(tmem_w + mb * kR, opnd_xw + kb * kOpK, kb == 0);
         umma_commit(g0_done);
+        SB_TRACE(a, 3);
         mbar_wait(hq_ready, tph);
         tc_fence_after();
+        SB_TRACE(a, 8);
         for (int mb = 0; mb < EM; mb++)
           for (int kb = 0; kb < EK; kb++) cons.mma(tmem_q + mb * kR, opnd_h + kb * kOpK, kb == 0);
         umma_commit(g1_done);
+        SB_TRACE(a, 9);
       }
     } else if (warp >= 4) {
       const int ew = warp - 4;
@@ -143,8 +149,10 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
             xv[mb][r] = a.x[o];
           }
         }
+        if (et == 0) SB_TRACE(a, 14);
         mbar_wait(g0_done, tph);
         tc_fence_after();
+        if (et == 0) SB_TRACE(a, 4);
 #pragma unroll
         for (int mb = 0; mb < EM; mb++) {
           uint32_t vf[8], vw[8];
@@ -165,8 +173,10 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
         }
       }
       named_bar_sync(1, kEpiThreads);
+      if (et == 0) SB_TRACE(a, 5);
       if (et < kR) ln_stats_row<E>(xs + et * XS, &stats[et], &stats[32 + et], a.eps);
       named_bar_sync(1, kEpiThreads);
+      if (et == 0) SB_TRACE(a, 6);
       {
         const float g = a.ln_scale[nf], b = a.ln_bias[nf];
 #pragma unroll 4
@@ -180,10 +190,12 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(hq_ready);
+      if (et == 0) SB_TRACE(a, 7);
 
       // ---- q = Wq h + bq -> global
       mbar_wait(g1_done, tph);
       tc_fence_after();
+      if (et == 0) SB_TRACE(a, 10);
 #pragma unroll
       for (int mb = 0; mb < EM; mb++) {
         uint32_t v[8];
@@ -197,11 +209,13 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
           if (grow < a.M) a.q_out[static_cast<size_t>(grow) * E + f] = dequant1(static_cast<int>(v[r]), a.um_q, pb);
         }
       }
+      if (et == 0) SB_TRACE(a, 11);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
   }
+  if (threadIdx.x == 0) SB_TRACE(a, 13);
   if (warp == 2) tmem_dealloc<512>(tmem);
 }
 

@@ -16,6 +16,7 @@
 namespace sb {
 
 constexpr int kRowTile = 32;
+constexpr int kTraceSlots = 128;  // debugging aid: per-CTA clock64() stamps of a kernel's phase boundaries
 
 // Attention output projection + residual + LayerNorm, then the feed-forward block with its own residual +
 // LayerNorm (encoder and decoder layers):  y = LN1(res + Wo a + bo);  z = LN2(y + W2 relu(W1 y + b1) + b2).
@@ -40,6 +41,7 @@ struct RowsFfnArgs {
   int n_zq;
   int zq_signed;                       // bit k: zq[k] receives the signed value instead of u8 = q + 127
   int M;
+  long long* trace;                    // optional phase timestamps (clock64), kTraceSlots per CTA; see SLIMT_B200_TRACE
 };
 
 // SSRU cell + query projection:  c = sigmoid(Wf x + bf) * c_prev + (1 - sigmoid(.)) * (W x);
@@ -60,6 +62,7 @@ struct DecSsruArgs {
   float* h_out;                        // f32 [M][E]
   float* q_out;                        // f32 [M][E]
   int M;
+  long long* trace;                    // optional phase timestamps, as above
 };
 
 // E = 256, F = 1536 (tiny) and E = 512, F = 2048 (base) are built.  Returns nonzero when unsupported.

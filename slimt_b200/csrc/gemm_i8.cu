@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(kThreads) gemm_i8_kernel(const __grid_constant
   using Cfg = TileCfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
 
   const GemmProblem& P = batch.prob[blockIdx.z];
   const int M = batch.M, N = batch.N, K = batch.K;

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kOutThreads, 1)
   constexpr int kABytes = kBM * kBK;        // one k-block of A
   constexpr int kBBytes = kOutBN * kBK;     // one k-block of B
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* smem_b = smem;                     // resident weight tile: KB k-blocks
   uint8_t* smem_a = smem + KB * kBBytes;      // ring of activation k-blocks
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + kOutStages * kABytes);

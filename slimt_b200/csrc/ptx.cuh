@@ -12,6 +12,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// 1024-byte alignment of the dynamic shared-memory base by pointer arithmetic on the __shared__ array itself, so
+// the compiler keeps the shared state space (LDS/STS) instead of falling back to generic loads and stores.
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* base) {
+  return base + ((1024u - (smem_u32(base) & 1023u)) & 1023u);
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

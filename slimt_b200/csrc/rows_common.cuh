@@ -9,6 +9,12 @@
 #include "fused_rows.cuh"
 #include "ptx.cuh"
 
+// phase stamp of the calling thread into the CTA's trace slots (no-op unless the launch carries a trace buffer)
+#define SB_TRACE(args, slot)                                                                  \
+  do {                                                                                        \
+    if ((args).trace) (args).trace[blockIdx.x * kTraceSlots + (slot)] = clock64();            \
+  } while (0)
+
 namespace sb {
 namespace rows {
 
@@ -33,15 +39,45 @@ __device__ __forceinline__ uint8_t quant_byte(float x, float aq, bool sgn) {
 // population variance, eps inside the square root).  Thread = row; rows are E + 1 floats apart (bank-conflict free).
 template <int E>
 __device__ __forceinline__ void ln_stats_row(const float* xr, float* mean_out, float* sigma_out, float eps) {
+  // The two sums are strict left-to-right chains (4 cycles per add); the loads of the next 16 elements are issued
+  // before the current 16 are added so that the chain never waits for shared memory.
+  constexpr int kB = 16;
+  static_assert(E % (2 * kB) == 0, "row length");
+  float a[kB], b[kB];
+#pragma unroll
+  for (int i = 0; i < kB; i++) a[i] = xr[i];
   float sum = 0.0f;
-#pragma unroll 8
-  for (int e = 0; e < E; e++) sum = __fadd_rn(sum, xr[e]);
+#pragma unroll 1
+  for (int e = 0; e < E; e += 2 * kB) {
+#pragma unroll
+    for (int i = 0; i < kB; i++) b[i] = xr[e + kB + i];
+#pragma unroll
+    for (int i = 0; i < kB; i++) sum = __fadd_rn(sum, a[i]);
+    const int nx = (e + 2 * kB < E) ? e + 2 * kB : 0;  // the last prefetch wraps to the row start: reused by pass 2
+#pragma unroll
+    for (int i = 0; i < kB; i++) a[i] = xr[nx + i];
+#pragma unroll
+    for (int i = 0; i < kB; i++) sum = __fadd_rn(sum, b[i]);
+  }
   const float mean = __fdiv_rn(sum, static_cast<float>(E));
   float sq = 0.0f;
-#pragma unroll 8
-  for (int e = 0; e < E; e++) {
-    const float d = __fsub_rn(xr[e], mean);
-    sq = __fadd_rn(sq, __fmul_rn(d, d));
+#pragma unroll 1
+  for (int e = 0; e < E; e += 2 * kB) {
+#pragma unroll
+    for (int i = 0; i < kB; i++) b[i] = xr[e + kB + i];
+#pragma unroll
+    for (int i = 0; i < kB; i++) {
+      const float d = __fsub_rn(a[i], mean);
+      sq = __fadd_rn(sq, __fmul_rn(d, d));
+    }
+    const int nx = (e + 2 * kB < E) ? e + 2 * kB : 0;
+#pragma unroll
+    for (int i = 0; i < kB; i++) a[i] = xr[nx + i];
+#pragma unroll
+    for (int i = 0; i < kB; i++) {
+      const float d = __fsub_rn(b[i], mean);
+      sq = __fadd_rn(sq, __fmul_rn(d, d));
+    }
   }
   *mean_out = mean;
   *sigma_out = __fsqrt_rn(__fadd_rn(__fdiv_rn(sq, static_cast<float>(E)), eps));
@@ -75,16 +111,27 @@ struct RingConsumer {
   uint64_t* empty;
   uint32_t it;
   int stages;
+  bool timing = false;     // tracing only: accumulate the cycles spent waiting for weight tiles
+  long long waited = 0;
+  long long* fine = nullptr;  // tracing only: 8 stamps of the next call (entry, tile landed, fence, 4 MMAs, commit)
   __device__ __forceinline__ void mma(uint32_t tmem_d, const uint8_t* opnd_kblock, bool first) {
     constexpr uint32_t idesc = make_idesc_i8_wa(128, R);
     const uint32_t s = it % stages, ph = (it / stages) & 1;
+    const long long t0 = timing ? clock64() : 0;
     mbar_wait(&full[s], ph);
+    if (timing) waited += clock64() - t0;
+    if (fine) fine[0] = t0, fine[1] = clock64();
     tc_fence_after();
+    if (fine) fine[2] = clock64();
     const uint64_t da = make_kmajor_sw128_desc(smem_u32(ring + s * kWTile));
     const uint64_t db = make_kmajor_sw128_desc(smem_u32(opnd_kblock));
 #pragma unroll
-    for (int k = 0; k < 4; k++) umma_i8(tmem_d, da + 2 * k, db + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+    for (int k = 0; k < 4; k++) {
+      umma_i8(tmem_d, da + 2 * k, db + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+      if (fine) fine[3 + k] = clock64();
+    }
     umma_commit(&empty[s]);
+    if (fine) fine[7] = clock64(), fine = nullptr;
     it++;
   }
 };

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
   constexpr int EK = L::EK, EM = L::EM, FM = L::FM, XS = L::XS, kOpK = L::kOpK;
   constexpr int RPW = R / 4;  // rows (TMEM columns) per epilogue warp: 16 warps = 4 lane quadrants x 4 column groups
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* ring = smem + L::ring;
   uint8_t* opnd_a = smem + L::opnd_a;
   uint8_t* opnd_y = smem + L::opnd_y;
@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::tmem_slot);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) SB_TRACE(a, 0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.map_a);
     tma_prefetch_desc(&a.map_wo);
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (threadIdx.x == 0) SB_TRACE(a, 1);
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_acc = tmem;             // EM blocks x R columns: accumulators of the Wo GEMM, then of FFN2
   const uint32_t tmem_ring = tmem + EM * R;   // kTS slots x R columns: FFN1 feature blocks
@@ -102,6 +104,8 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
   uint32_t blocks = 0;   // FFN1 feature blocks so far: position in the TMEM slot ring and the operand ring (per role)
   RingProducer prod{ring, full, empty, 0, L::kStages};
   RingConsumer<R> cons{ring, full, empty, 0, L::kStages};
+  cons.timing = a.trace != nullptr;
+  long long waited_fq = 0;
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, iter++) {
     const int row0 = tile * R;
@@ -124,31 +128,48 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
       // ===== MMA issuer
       if (lane == 0) {
         mbar_wait(a_full, tph);
+        SB_TRACE(a, 2);
         for (int mb = 0; mb < EM; mb++)
           for (int kb = 0; kb < EK; kb++) cons.mma(tmem_acc + mb * R, opnd_a + kb * kOpK, kb == 0);
         umma_commit(g0_done);
+        SB_TRACE(a, 3);
         mbar_wait(yq_ready, tph);
         tc_fence_after();
+        SB_TRACE(a, 8);
         for (int st = 0; st < FM + kLook; st++) {
           if (st < FM) {  // FFN1 feature block st -> TMEM slot
             const uint32_t n = blocks + st;
             const uint32_t s = n % L::kTS, ph = (n / L::kTS) & 1;
             mbar_wait(&slot_empty[s], ph ^ 1);
             tc_fence_after();
-            for (int kb = 0; kb < EK; kb++) cons.mma(tmem_ring + s * R, opnd_y + kb * kOpK, kb == 0);
+            for (int kb = 0; kb < EK; kb++) {
+              if (a.trace && st == 5 && kb < 2) cons.fine = a.trace + blockIdx.x * kTraceSlots + 64 + 8 * kb;
+              cons.mma(tmem_ring + s * R, opnd_y + kb * kOpK, kb == 0);
+            }
             umma_commit(&slot_full[s]);
+            if (st < 12) SB_TRACE(a, 16 + st);
           }
           if (st >= kLook) {  // FFN2 k-step kb2 = st - kLook, fed by the requantised block kb2
             const int kb2 = st - kLook;
             const uint32_t n = blocks + kb2;
             const uint32_t s = n % L::kFS, ph = (n / L::kFS) & 1;
+            const long long t0 = cons.timing ? clock64() : 0;
             mbar_wait(&fq_full[s], ph);
+            if (cons.timing) waited_fq += clock64() - t0;
             tc_fence_after();
-            for (int mb = 0; mb < EM; mb++) cons.mma(tmem_acc + mb * R, opnd_f + s * kOpK, kb2 == 0);
+            for (int mb = 0; mb < EM; mb++) {
+              if (a.trace && kb2 == 3 && mb < 2) cons.fine = a.trace + blockIdx.x * kTraceSlots + 80 + 8 * mb;
+              cons.mma(tmem_acc + mb * R, opnd_f + s * kOpK, kb2 == 0);
+            }
             umma_commit(&fq_free[s]);
+            if (kb2 < 12) SB_TRACE(a, 28 + kb2);
           }
         }
         umma_commit(g2_done);
+        if (a.trace) {  // slots 14, 15: cycles the MMA thread spent waiting for weight tiles / requantised blocks
+          a.trace[blockIdx.x * kTraceSlots + 14] = a.trace[blockIdx.x * kTraceSlots] + cons.waited;
+          a.trace[blockIdx.x * kTraceSlots + 15] = a.trace[blockIdx.x * kTraceSlots] + waited_fq;
+        }
         blocks += FM;
       }
     } else if (warp >= 4) {
@@ -175,6 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
       // ---- epilogue 0: x = (Wo a + bo) + res -> xs
       mbar_wait(g0_done, tph);
       tc_fence_after();
+      if (et == 0) SB_TRACE(a, 4);
 #pragma unroll 1
       for (int mb = 0; mb < EM; mb++) {
         uint32_t v[RPW];
@@ -193,8 +215,10 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
           xs[(cg * RPW + r) * XS + f] = __fadd_rn(dequant1(static_cast<int>(v[r]), a.um_o, pb), res[r]);
       }
       named_bar_sync(1, kEpiThreads);
+      if (et == 0) SB_TRACE(a, 5);
       if (et < R) ln_stats_row<E>(xs + et * XS, &stats[et], &stats[R + et], a.eps);
       named_bar_sync(1, kEpiThreads);
+      if (et == 0) SB_TRACE(a, 6);
       // y = LN1(x): residual of the FFN block (kept in xs, or parked in global when xs is about to be reused by
       // the operand ring) and the u8 operand of W1
       {
@@ -217,6 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
       if constexpr (L::kParkY) named_bar_sync(1, kEpiThreads);  // xs is dead from here: the operand ring may overwrite it
       __syncwarp();
       if (lane == 0) mbar_arrive(yq_ready);
+      if (et == 0) SB_TRACE(a, 7);
 
       // ---- epilogue 1: per FFN1 feature block, relu + requantise -> operand ring slot
 #pragma unroll 1
@@ -226,6 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
         const uint32_t fs = n % L::kFS, fph = (n / L::kFS) & 1;
         mbar_wait(&slot_full[ts], tph2);
         tc_fence_after();
+        if (et == 0 && j < 12) SB_TRACE(a, 40 + j);
         uint32_t v[RPW];
         tmem_ldn_nowait<RPW>(tmem_ring + lane_sel + ts * R + cg * RPW, v);
         const float pb = a.pb_1[j * 128 + kk];
@@ -244,12 +270,14 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&fq_full[fs]);
+        if (et == 0 && j < 12) SB_TRACE(a, 52 + j);
       }
       blocks += FM;
 
       // ---- epilogue 2: x = (W2 f + b2) + y -> xs; z = LN2(x) -> global
       mbar_wait(g2_done, tph);
       tc_fence_after();
+      if (et == 0) SB_TRACE(a, 9);
 #pragma unroll 1
       for (int mb = 0; mb < EM; mb++) {
         uint32_t v[RPW];
@@ -273,8 +301,10 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
       }
       tc_fence_before();
       named_bar_sync(1, kEpiThreads);
+      if (et == 0) SB_TRACE(a, 10);
       if (et < R) ln_stats_row<E>(xs + et * XS, &stats[et], &stats[R + et], a.eps);
       named_bar_sync(1, kEpiThreads);
+      if (et == 0) SB_TRACE(a, 11);
       {
         const float g = a.ln2_scale[nf], b = a.ln2_bias[nf];
         // consumers' quantised copies: pointers and multipliers in registers, sign handling decided once
@@ -300,12 +330,14 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
             if (zp[k]) zp[k][o] = static_cast<uint8_t>(quantize1(z, za[k]) - zsub[k]);
         }
       }
+      if (et == 0) SB_TRACE(a, 12);
     }
     // all roles meet before the tile's buffers and once-per-tile barriers are reused
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
   }
+  if (threadIdx.x == 0) SB_TRACE(a, 13);
   if (warp == 2) tmem_dealloc<512>(tmem);
 }
 
