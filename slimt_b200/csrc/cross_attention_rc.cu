@@ -1,0 +1,321 @@
+// Decoder cross-attention that RECOMPUTES the key/value projections on the tensor cores every step instead of
+// streaming an f32 K/V cache from HBM (reference: Attention::forward, slimt/Modules.cc:287-319 — which also
+// re-projects K and V on every step, :244-249 — and scaled_dot_product_attention :24-86).
+//
+// Why: at tiny11 sizes the cached path reads 2 * S * E * 4 = 64 KB per sentence per layer per step and is pinned to
+// the HBM roofline.  The projections' INPUT, the encoder output quantised for Wk and Wv (PrepareA bytes), is 4x
+// smaller (2 * S * E bytes), the int8 MMAs that rebuild K = dequant(qa_k Wk) and V = dequant(qa_v Wv) are nearly
+// free on tcgen05, and the f32 values they produce are the very ones the cache would have held: the int32
+// accumulators are exact and the dequantisation is the same two roundings.
+//
+// One persistent CTA per SM walks groups of 4 sentences (4 x 32 key rows = the 128 TMEM lanes); Wk and Wv (64 KB
+// each) stay resident in shared memory for the whole launch.
+//   K phase   D_k[key row][feature]   = qa_k tile (A, M = 128) x Wk (B, N = 256): TMEM lane = key, so a consumer
+//             thread dequantises its key's 32 features of a head and runs the reference's sequential fma chain
+//             against q; softmax across the 32 lanes of the warp (max by shuffle, sum in key order).
+//   V phase   D_v[feature][key row]   = Wv (A, M = 128 per block) x qa_v tile (B, N = 128): TMEM lane = feature, so
+//             a thread accumulates its output feature over the keys in order, probabilities broadcast from smem.
+// The MMA of the next phase overlaps the drain of the current one (D_k and D_v are separate TMEM regions).
+// Supported: E = 256, 8 heads of 32, S <= 32.  Everything else uses the cached kernel (cross_attention.cu).
+#include <stdio.h>
+
+#include "exact_math.cuh"
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace sb {
+
+namespace {
+
+constexpr int kE = 256, kH = 8, kDH = 32;
+constexpr int kGroup = 4;                  // sentences per group
+constexpr int kKeys = 32;                  // key rows per sentence (box rows)
+constexpr int kConsWarps = 16;
+constexpr int kConsThreads = kConsWarps * 32;
+constexpr int kThreadsRc = 128 + kConsThreads;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 tables, 4..19 consumers
+
+struct Smem {
+  static constexpr int wk = 0;                        // 2 k-blocks x [256 features x 128 B]
+  static constexpr int wv = wk + 64 * 1024;
+  static constexpr int ak = wv + 64 * 1024;           // 2 k-blocks x [128 key rows x 128 B]
+  static constexpr int av = ak + 32 * 1024;
+  static constexpr int qs = av + 32 * 1024;           // f32 [4][256]
+  static constexpr int ps = qs + kGroup * kE * 4;     // f32 [4][8][32]
+  static constexpr int pbk = ps + kGroup * kH * kKeys * 4;  // f32 [256]
+  static constexpr int exp_tab = pbk + kE * 4;        // u64 [32]
+  static constexpr int bars = exp_tab + 32 * 8;
+  // w_full ak_full av_full ak_free av_free k_done v_done k_drained v_drained
+  static constexpr int n_bars = 9;
+  static constexpr int tmem_slot = bars + n_bars * 8;
+  static constexpr int total = tmem_slot + 16 + 1024;
+};
+
+__global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const __grid_constant__ CrossRcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  uint8_t* s_wk = smem + Smem::wk;
+  uint8_t* s_wv = smem + Smem::wv;
+  uint8_t* s_ak = smem + Smem::ak;
+  uint8_t* s_av = smem + Smem::av;
+  float* s_q = reinterpret_cast<float*>(smem + Smem::qs);
+  float* s_p = reinterpret_cast<float*>(smem + Smem::ps);
+  float* s_pbk = reinterpret_cast<float*>(smem + Smem::pbk);
+  uint64_t* exp_tab = reinterpret_cast<uint64_t*>(smem + Smem::exp_tab);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
+  uint64_t* w_full = bars;
+  uint64_t* ak_full = bars + 1;
+  uint64_t* av_full = bars + 2;
+  uint64_t* ak_free = bars + 3;
+  uint64_t* av_free = bars + 4;
+  uint64_t* k_done = bars + 5;
+  uint64_t* v_done = bars + 6;
+  uint64_t* k_drained = bars + 7;
+  uint64_t* v_drained = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::tmem_slot);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.map_ak);
+    tma_prefetch_desc(&a.map_av);
+    tma_prefetch_desc(&a.map_wk);
+    tma_prefetch_desc(&a.map_wv);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 7; i++) mbar_init(&bars[i], 1);
+    mbar_init(k_drained, kConsWarps);
+    mbar_init(v_drained, kConsWarps);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 3) {
+    exp_tab[lane] = kExp2fTab[lane];
+    for (int i = lane; i < kE; i += 32) s_pbk[i] = a.pb_k[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_k = tmem;         // 256 columns: features
+  const uint32_t tmem_v = tmem + 256;   // 2 blocks x 128 columns: key rows of the group
+
+  const int n_groups = (a.B + kGroup - 1) / kGroup;
+
+  if (warp == 0) {
+    // ===== TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(w_full, 128 * 1024);
+      for (int kb = 0; kb < 2; kb++)
+        for (int half = 0; half < 2; half++) {
+          tma_load_2d(s_wk + kb * 32768 + half * 16384, &a.map_wk, w_full, kb * 128, half * 128);
+          tma_load_2d(s_wv + kb * 32768 + half * 16384, &a.map_wv, w_full, kb * 128, half * 128);
+        }
+      uint32_t it = 0;
+      for (int g = blockIdx.x; g < n_groups; g += gridDim.x, it++) {
+        const uint32_t ph = it & 1;
+        const int b0 = g * kGroup;
+        mbar_wait(ak_free, ph ^ 1);
+        mbar_expect_tx(ak_full, 32 * 1024);
+        for (int kb = 0; kb < 2; kb++)
+          for (int j = 0; j < kGroup; j++) {
+            const int b = b0 + j < a.B ? b0 + j : b0;  // tail group: repeat a valid sentence, its lanes are ignored
+            tma_load_2d(s_ak + kb * 16384 + j * 4096, &a.map_ak, ak_full, kb * 128, b * a.T);
+          }
+        mbar_wait(av_free, ph ^ 1);
+        mbar_expect_tx(av_full, 32 * 1024);
+        for (int kb = 0; kb < 2; kb++)
+          for (int j = 0; j < kGroup; j++) {
+            const int b = b0 + j < a.B ? b0 + j : b0;
+            tma_load_2d(s_av + kb * 16384 + j * 4096, &a.map_av, av_full, kb * 128, b * a.T);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_k = make_idesc_i8(128, 256);     // A = u8 key rows, B = s8 Wk
+      constexpr uint32_t idesc_v = make_idesc_i8_wa(128, 128);  // A = s8 Wv block, B = u8 key rows
+      mbar_wait(w_full, 0);
+      uint32_t it = 0;
+      for (int g = blockIdx.x; g < n_groups; g += gridDim.x, it++) {
+        const uint32_t ph = it & 1;
+        mbar_wait(ak_full, ph);
+        mbar_wait(k_drained, ph ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < 2; kb++) {
+          const uint64_t da = make_kmajor_sw128_desc(smem_u32(s_ak + kb * 16384));
+          const uint64_t db = make_kmajor_sw128_desc(smem_u32(s_wk + kb * 32768));
+#pragma unroll
+          for (int k = 0; k < 4; k++) umma_i8(tmem_k, da + 2 * k, db + 2 * k, idesc_k, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(k_done);
+        umma_commit(ak_free);
+        mbar_wait(av_full, ph);
+        mbar_wait(v_drained, ph ^ 1);
+        tc_fence_after();
+        for (int mb = 0; mb < 2; mb++)
+          for (int kb = 0; kb < 2; kb++) {
+            const uint64_t da = make_kmajor_sw128_desc(smem_u32(s_wv + kb * 32768 + mb * 16384));
+            const uint64_t db = make_kmajor_sw128_desc(smem_u32(s_av + kb * 16384));
+#pragma unroll
+            for (int k = 0; k < 4; k++) umma_i8(tmem_v + mb * 128, da + 2 * k, db + 2 * k, idesc_v, (kb | k) ? 1u : 0u);
+          }
+        umma_commit(v_done);
+        umma_commit(av_free);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== consumers
+    const int cw = warp - 4;
+    const int qd = warp & 3;   // TMEM lane quadrant of this warp
+    const int sub = cw >> 2;   // 0..3: which share of the quadrant's work
+    const int ct = threadIdx.x - 128;
+    const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
+    // V phase: this thread's output feature
+    const int v_mb = sub & 1;
+    const int v_feat = v_mb * 128 + qd * 32 + lane;
+    const int v_head = v_mb * 4 + qd;
+    const float pbv = a.pb_v[v_feat];
+    uint32_t it = 0;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x, it++) {
+      const uint32_t ph = it & 1;
+      const int b0 = g * kGroup;
+      // the group's query rows
+      for (int i = ct; i < kGroup * kE; i += kConsThreads) {
+        const int b = b0 + i / kE;
+        s_q[i] = b < a.B ? a.q[static_cast<size_t>(b) * kE + (i % kE)] : 0.0f;
+      }
+      named_bar_sync(1, kConsThreads);
+
+      // ---- K phase: quadrant = sentence, lane = key, two heads per warp
+      {
+        const int j = qd;
+        const int b = b0 + j;
+        const int len = b < a.B ? min(static_cast<int>(a.lengths[b]), a.T) : 0;
+        const bool valid = lane < len;
+        mbar_wait(k_done, ph);
+        tc_fence_after();
+        uint32_t v0[32], v1[32];
+        const int h0 = sub * 2;
+        tmem_ld32_nowait(tmem_k + lane_sel + h0 * 32, v0);
+        tmem_ld32_nowait(tmem_k + lane_sel + h0 * 32 + 32, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(k_drained);
+        float sc[2];
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          const float* qh = s_q + j * kE + (h0 + hh) * kDH;
+          const float* pbh = s_pbk + (h0 + hh) * kDH;
+          float acc = 0.0f;
+#pragma unroll
+          for (int d = 0; d < kDH; d += 4) {
+            const float4 qq = *reinterpret_cast<const float4*>(qh + d);
+            const float4 pb = *reinterpret_cast<const float4*>(pbh + d);
+            const uint32_t* vv = hh == 0 ? v0 : v1;
+            acc = fmaf(qq.x, dequant1(static_cast<int>(vv[d]), a.um_k, pb.x), acc);
+            acc = fmaf(qq.y, dequant1(static_cast<int>(vv[d + 1]), a.um_k, pb.y), acc);
+            acc = fmaf(qq.z, dequant1(static_cast<int>(vv[d + 2]), a.um_k, pb.z), acc);
+            acc = fmaf(qq.w, dequant1(static_cast<int>(vv[d + 3]), a.um_k, pb.w), acc);
+          }
+          sc[hh] = __fmul_rn(a.dk, acc);
+        }
+        // softmax over the sentence's keys (slimt/TensorOps.cc:282-315): max, exp, sum in key order, divide
+        float mx[2], e[2], sum[2];
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          mx[hh] = valid ? sc[hh] : -3.402823466e+38f;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], o));
+          e[hh] = valid ? expf_glibc_nonpos_tab(__fsub_rn(sc[hh], mx[hh]), exp_tab) : 0.0f;
+          s_p[(j * kH + h0 + hh) * kKeys + lane] = e[hh];
+          sum[hh] = 0.0f;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int l = 0; l < kKeys; l += 4) {
+#pragma unroll
+          for (int hh = 0; hh < 2; hh++) {
+            const float4 t = *reinterpret_cast<const float4*>(s_p + (j * kH + h0 + hh) * kKeys + l);
+            sum[hh] = __fadd_rn(sum[hh], t.x);
+            sum[hh] = __fadd_rn(sum[hh], t.y);
+            sum[hh] = __fadd_rn(sum[hh], t.z);
+            sum[hh] = __fadd_rn(sum[hh], t.w);
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          const float p = valid ? __fdiv_rn(e[hh], sum[hh]) : 0.0f;
+          s_p[(j * kH + h0 + hh) * kKeys + lane] = p;
+          if (a.attn_head0 != nullptr && h0 + hh == 0 && b < a.B && lane < a.T)
+            a.attn_head0[static_cast<size_t>(b) * a.T + lane] = p;
+        }
+      }
+      named_bar_sync(1, kConsThreads);
+
+      // ---- V phase: lane = output feature, two sentences per warp
+      {
+        mbar_wait(v_done, ph);
+        tc_fence_after();
+        uint32_t v0[32], v1[32];
+        const int j0 = (sub >> 1) * 2;
+        tmem_ld32_nowait(tmem_v + lane_sel + v_mb * 128 + j0 * 32, v0);
+        tmem_ld32_nowait(tmem_v + lane_sel + v_mb * 128 + j0 * 32 + 32, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(v_drained);
+#pragma unroll
+        for (int jj = 0; jj < 2; jj++) {
+          const int j = j0 + jj;
+          const int b = b0 + j;
+          if (b >= a.B) continue;
+          const int len = min(static_cast<int>(a.lengths[b]), a.T);
+          const float* pr = s_p + (j * kH + v_head) * kKeys;
+          const uint32_t* vv = jj == 0 ? v0 : v1;
+          float acc = 0.0f;
+          if (len == kKeys) {
+#pragma unroll
+            for (int l = 0; l < kKeys; l += 4) {
+              const float4 p = *reinterpret_cast<const float4*>(pr + l);
+              acc = fmaf(p.x, dequant1(static_cast<int>(vv[l]), a.um_v, pbv), acc);
+              acc = fmaf(p.y, dequant1(static_cast<int>(vv[l + 1]), a.um_v, pbv), acc);
+              acc = fmaf(p.z, dequant1(static_cast<int>(vv[l + 2]), a.um_v, pbv), acc);
+              acc = fmaf(p.w, dequant1(static_cast<int>(vv[l + 3]), a.um_v, pbv), acc);
+            }
+          } else {
+            // ragged sentence: only its own keys take part (the rows beyond belong to the next sentence)
+#pragma unroll
+            for (int l = 0; l < kKeys; l++) {
+              if (l < len) acc = fmaf(pr[l], dequant1(static_cast<int>(vv[l]), a.um_v, pbv), acc);
+            }
+          }
+          const size_t off = static_cast<size_t>(b) * kE + v_feat;
+          if (a.out_f32) a.out_f32[off] = acc;
+          for (int k = 0; k < a.qo.n; k++) a.qo.ptr[k][off] = static_cast<int8_t>(quantize1(acc, a.qo.aq[k]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace
+
+bool cross_attention_rc_supported(int E, int H, int dh, int S) { return E == kE && H == kH && dh == kDH && S >= 1 && S <= kKeys; }
+
+int launch_cross_attention_rc(const CrossRcArgs& a, int num_sms, cudaStream_t stream) {
+  if (a.B == 0) return 0;
+  const int groups = (a.B + kGroup - 1) / kGroup;
+  if (cudaFuncSetAttribute(cross_attention_rc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total) !=
+      cudaSuccess)
+    return 1;
+  cross_attention_rc_kernel<<<groups < num_sms ? groups : num_sms, kThreadsRc, Smem::total, stream>>>(a);
+  return 0;
+}
+
+}  // namespace sb

@@ -738,8 +738,16 @@ int model_forward(Model& m, ForwardArgs& a) {
     c.d2h_bytes += 4ul * R * E;
   }
 
-  // ---- cross-attention K/V, once per batch (the reference re-projects them every step: Modules.cc:244-249)
-  for (int l = 0; l < Ld; l++) {
+  // ---- cross-attention K/V.  The reference re-projects them every step (Modules.cc:244-249); so does the
+  // recompute kernel (tensor cores, from the u8 encoder output); otherwise they are projected once and cached.
+  const char* ca_env = getenv("SLIMT_B200_CROSS");
+  const bool cross_rc = cross_attention_rc_supported(E, H, dh, T) && !(ca_env && strcmp(ca_env, "cached") == 0);
+  std::vector<CUtensorMap> mapAk(Ld), mapAv(Ld);
+  if (cross_rc) {
+    for (int l = 0; l < Ld; l++)
+      if (c.make_map(&mapAk[l], qa[2 * l], R, E, 32) || c.make_map(&mapAv[l], qa[2 * l + 1], R, E, 32)) return 1;
+  }
+  for (int l = 0; l < Ld && !cross_rc; l++) {
     GemmCall g(&c, "dec_gemm_cross_kv_f32", R, E, E, EPI_F32, 2);
     GemmProblem* pk = g.add(qa[2 * l], m.dec[l].ctx.k);
     GemmProblem* pv = g.add(qa[2 * l + 1], m.dec[l].ctx.v);
@@ -889,7 +897,25 @@ int model_forward(Model& m, ForwardArgs& a) {
           return 1;
         }
       }
-      {
+      if (cross_rc) {
+        CrossRcArgs k{};
+        k.map_ak = mapAk[l], k.map_av = mapAv[l];
+        k.map_wk = L.ctx.k.map128, k.map_wv = L.ctx.v.map128;
+        k.pb_k = L.ctx.k.pb, k.pb_v = L.ctx.v.pb;
+        k.um_k = L.ctx.k.um, k.um_v = L.ctx.v.um;
+        k.q = qd, k.lengths = d_lengths, k.B = B, k.T = T;
+        k.dk = static_cast<float>(1.0 / std::sqrt(static_cast<double>(dh)));
+        k.out_f32 = nullptr;
+        k.qo = qouts();
+        qadd(k.qo, caq, L.ctx.o.aq);
+        k.attn_head0 = last ? d_align : nullptr;
+        const double Bd = B, Ed = E;
+        LaunchScope ls(c, "dec_cross_attention_rc", 2.0 * Bd * 32.0 * Ed * 2.0 * Ed, 2.0 * Bd * T * Ed + 2.0 * Ed * Ed + 5.0 * Bd * Ed);
+        if (launch_cross_attention_rc(k, c.num_sms, s)) {
+          set_error("recompute cross-attention launch failed");
+          return 1;
+        }
+      } else {
         QuantOuts q = qouts();
         qadd(q, caq, L.ctx.o.aq);
         LaunchScope ls(c, "dec_cross_attention", 0, 8.0 * src_tokens * E + 5.0 * B * E);

@@ -38,6 +38,25 @@ void launch_cross_attention(const CUtensorMap& mapK, const CUtensorMap& mapV, co
                             const uint32_t* lengths, int B, int S, int H, int dh, int num_sms, float* out_f32,
                             QuantOuts q, float* attn_head0, cudaStream_t stream);
 
+// The same attention with K and V re-projected from the quantised encoder output on the tensor cores every step
+// instead of read from an f32 cache (cross_attention_rc.cu): 4x less HBM traffic, bit-identical results.
+struct CrossRcArgs {
+  CUtensorMap map_ak, map_av;  // u8 [B*S][E], box {128 B, 32 rows}: encoder output quantised with Wk's / Wv's a_quant
+  CUtensorMap map_wk, map_wv;  // s8 [E][E], box {128 B, 128 rows}
+  const float* pb_k;           // prepared biases
+  const float* pb_v;
+  float um_k, um_v;            // 1 / (a_quant * b_quant)
+  const float* q;              // f32 [B][E]
+  const uint32_t* lengths;
+  int B, T;
+  float dk;                    // 1 / sqrt(head size)
+  float* out_f32;              // optional f32 [B][E]
+  QuantOuts qo;                // int8 copies of the output (Wo's operand)
+  float* attn_head0;           // optional [B][T]
+};
+bool cross_attention_rc_supported(int E, int H, int dh, int S);
+int launch_cross_attention_rc(const CrossRcArgs& a, int num_sms, cudaStream_t stream);
+
 // SSRU cell tail (slimt/Modules.cc:190-235): c = highway(c_prev, Wx, f); h = LN(x + relu(c)); state <- c.
 void launch_ssru_ln(const float* f, const float* wx, float* state, const float* x, const float* ln_scale,
                     const float* ln_bias, float eps, int B, int E, float* h, QuantOuts q, cudaStream_t stream);

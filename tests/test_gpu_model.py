@@ -67,6 +67,26 @@ def test_forward_ragged_batches(tiny_gpu, shape):
     assert np.array_equal(fused["step_tokens"], ref["step_tokens"]) and fused["target_tokens"] == out["target_tokens"]
 
 
+@pytest.mark.parametrize("shape", [(37, 32), (9, 20), (4, 32)])
+def test_cross_attention_recompute_equals_cached_path(tiny_gpu, shape, monkeypatch):
+    """S <= 32 batches re-project K/V on the tensor cores every step (cross_attention_rc.cu); forcing the cached
+    f32 K/V kernel must give the same bits, and both must equal the oracle."""
+    m, orc = tiny_gpu
+    B, T = shape
+    sents = synth.make_sentences(B, (1, T), seed=7 * B + T)
+    sents[0] = synth.make_sentences(1, T, seed=2)[0]
+    sents[-1] = synth.make_sentences(1, T, seed=3)[0]
+    tokens, lengths = util.pad_batch(sents)
+    ref = orc.forward(tokens, lengths, keep=True)
+    rc = m.forward(tokens, lengths, want_logits=True, want_alignment=True)
+    monkeypatch.setenv("SLIMT_B200_CROSS", "cached")
+    cached = m.forward(tokens, lengths, want_logits=True, want_alignment=True)
+    monkeypatch.delenv("SLIMT_B200_CROSS")
+    _compare(rc, ref, lengths, T)
+    _compare(cached, ref, lengths, T)
+    assert np.array_equal(rc["logits"], cached["logits"])
+
+
 def test_forward_with_shortlist(tiny_gpu, shortlist_assets):
     m, orc = tiny_gpu
     fr, offs, lists = shortlist_assets[1]
