@@ -53,8 +53,10 @@ def test_golden_forward(gpu_ctx, name, tmp_path):
     m.close()
 
 
-@pytest.mark.parametrize("shape", [(8, 16), (5, 9), (1, 1), (3, 33), (130, 7)])
+@pytest.mark.parametrize("shape", [(8, 16), (5, 9), (1, 1), (3, 33), (130, 7), (6, 64), (3, 100), (2, 256)])
 def test_forward_ragged_batches(tiny_gpu, shape):
+    """Includes the long end of BASELINE.json's mixed-length sweep (8-256 tokens): keys beyond one 32-row box,
+    the cached K/V cross-attention path and hundreds of decode steps."""
     m, orc = tiny_gpu
     B, T = shape
     sents = synth.make_sentences(B, (1, T), seed=B * 100 + T)

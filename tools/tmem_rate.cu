@@ -27,8 +27,9 @@ __global__ void __launch_bounds__(512, 1) ld_rate(int iters, long long* cycles, 
     tmem_ld32_nowait(addr, v);
     if (PIPE == 2) tmem_ld32_nowait(addr + 32, w);
     tmem_ld_wait();
-    acc += v[i & 31];
-    if (PIPE == 2) acc += w[i & 31];
+    // fixed register indices: a dynamic index would park the arrays in local memory and time the spill instead
+    acc += v[0] ^ v[13] ^ v[31];
+    if (PIPE == 2) acc += w[0] ^ w[13] ^ w[31];
   }
   __syncthreads();
   long long t1 = clock64();
