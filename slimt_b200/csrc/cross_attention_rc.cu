@@ -94,6 +94,8 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_k = tmem;         // 256 columns: features
   const uint32_t tmem_v = tmem + 256;   // 2 blocks x 128 columns: key rows of the group
@@ -175,23 +177,45 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
     const int v_feat = v_mb * 128 + qd * 32 + lane;
     const int v_head = v_mb * 4 + qd;
     const float pbv = a.pb_v[v_feat];
+    // Global inputs of a group (its query rows and sentence lengths) are fetched one group ahead into registers, so
+    // their latency hides behind the previous group's arithmetic instead of opening every iteration.
+    static_assert(kGroup * kE == 2 * kConsThreads, "two query floats per consumer thread");
+    const int vj0 = (sub >> 1) * 2;
+    float q_nx[2];
+    int len_nx[3];  // K phase: sentence qd; V phase: sentences vj0, vj0 + 1
+    auto fetch_group = [&](int g) {
+      const int b0 = g * kGroup;
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const int i = ct + r * kConsThreads;
+        const int b = b0 + i / kE;
+        q_nx[r] = (g < n_groups && b < a.B) ? __ldg(a.q + static_cast<size_t>(b) * kE + (i % kE)) : 0.0f;
+      }
+      const int js[3] = {qd, vj0, vj0 + 1};
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const int b = b0 + js[r];
+        len_nx[r] = (g < n_groups && b < a.B) ? min(static_cast<int>(__ldg(a.lengths + b)), a.T) : 0;
+      }
+    };
+    fetch_group(blockIdx.x);
     uint32_t it = 0;
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x, it++) {
       const uint32_t ph = it & 1;
       const int b0 = g * kGroup;
-      // the group's query rows
-      for (int i = ct; i < kGroup * kE; i += kConsThreads) {
-        const int b = b0 + i / kE;
-        s_q[i] = b < a.B ? a.q[static_cast<size_t>(b) * kE + (i % kE)] : 0.0f;
-      }
+      // the group's query rows (s_q is free: the previous group's K phase ended before its mid-group barrier)
+      s_q[ct] = q_nx[0];
+      s_q[ct + kConsThreads] = q_nx[1];
+      const int len_k = len_nx[0];
+      const int len_v[2] = {len_nx[1], len_nx[2]};
+      fetch_group(g + gridDim.x);
       named_bar_sync(1, kConsThreads);
 
       // ---- K phase: quadrant = sentence, lane = key, two heads per warp
       {
         const int j = qd;
         const int b = b0 + j;
-        const int len = b < a.B ? min(static_cast<int>(a.lengths[b]), a.T) : 0;
-        const bool valid = lane < len;
+        const bool valid = lane < len_k;
         mbar_wait(k_done, ph);
         tc_fence_after();
         uint32_t v0[32], v1[32];
@@ -259,7 +283,7 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
         mbar_wait(v_done, ph);
         tc_fence_after();
         uint32_t v0[32], v1[32];
-        const int j0 = (sub >> 1) * 2;
+        const int j0 = vj0;
         tmem_ld32_nowait(tmem_v + lane_sel + v_mb * 128 + j0 * 32, v0);
         tmem_ld32_nowait(tmem_v + lane_sel + v_mb * 128 + j0 * 32 + 32, v1);
         tmem_ld_wait();
@@ -271,7 +295,7 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
           const int j = j0 + jj;
           const int b = b0 + j;
           if (b >= a.B) continue;
-          const int len = min(static_cast<int>(a.lengths[b]), a.T);
+          const int len = len_v[jj];
           const float* pr = s_p + (j * kH + v_head) * kKeys;
           const uint32_t* vv = jj == 0 ? v0 : v1;
           float acc = 0.0f;
@@ -314,8 +338,8 @@ int launch_cross_attention_rc(const CrossRcArgs& a, int num_sms, cudaStream_t st
   if (cudaFuncSetAttribute(cross_attention_rc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total) !=
       cudaSuccess)
     return 1;
-  cross_attention_rc_kernel<<<groups < num_sms ? groups : num_sms, kThreadsRc, Smem::total, stream>>>(a);
-  return 0;
+  return launch_pdl(cross_attention_rc_kernel, dim3(groups < num_sms ? groups : num_sms), dim3(kThreadsRc), Smem::total, stream,
+                    a) != cudaSuccess;
 }
 
 }  // namespace sb

@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
   if (threadIdx.x == 0) SB_TRACE(a, 1);
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_f = tmem;                    // gate pre-activations Wf x
@@ -228,7 +230,7 @@ int launch_rows(Kern kern, const Args& a, size_t smem, cudaStream_t stream) {
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  kern<<<tiles < sms ? tiles : sms, kThreads, smem, stream>>>(a);
+  if (launch_pdl(kern, dim3(tiles < sms ? tiles : sms), dim3(kThreads), smem, stream, a) != cudaSuccess) return 1;
   return 0;
 }
 

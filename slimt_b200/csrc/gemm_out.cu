@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(kOutThreads, 1)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -281,11 +283,15 @@ int launch_gemm_out_argmax(const CUtensorMap& tma_a, const CUtensorMap& tma_b, c
   if (KB == 2) {
     auto kern = out_argmax_kernel<2>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    kern<<<grid, kOutThreads, smem, stream>>>(tma_a, tma_b, pb, c127, dmax, um, eta, M, N, best);
+    if (launch_pdl(kern, dim3(grid), dim3(kOutThreads), smem, stream, tma_a, tma_b, pb, c127, dmax, um, eta, M, N, best) !=
+        cudaSuccess)
+      return 1;
   } else if (KB == 4) {
     auto kern = out_argmax_kernel<4>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    kern<<<grid, kOutThreads, smem, stream>>>(tma_a, tma_b, pb, c127, dmax, um, eta, M, N, best);
+    if (launch_pdl(kern, dim3(grid), dim3(kOutThreads), smem, stream, tma_a, tma_b, pb, c127, dmax, um, eta, M, N, best) !=
+        cudaSuccess)
+      return 1;
   } else {
     return 1;
   }

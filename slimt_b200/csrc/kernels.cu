@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include "exact_math.cuh"
+#include "ptx.cuh"
 
 namespace sb {
 
@@ -182,6 +183,8 @@ __global__ void finalize_step_kernel(unsigned long long* __restrict__ best, cons
                                      const float* __restrict__ pos0, int B, int E, float* __restrict__ x, QuantOuts q) {
   __shared__ uint32_t s_next;
   const int b = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x == 0) {
     const unsigned long long packed = best[b];
     const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(packed & 0xFFFFFFFFull);
@@ -314,8 +317,8 @@ void launch_finalize_step(unsigned long long* best, const uint32_t* shortlist, c
                           uint32_t* step_tokens, uint8_t* done, uint32_t* tgt_len, int* n_done, const int8_t* emb_q, float inv_qm,
                           float sqrt_e, const float* pos0, int B, int E, float* x, QuantOuts q, cudaStream_t stream) {
   if (B == 0) return;
-  finalize_step_kernel<<<B, 64, 0, stream>>>(best, shortlist, forced, step, step_tokens, done, tgt_len, n_done, emb_q, inv_qm,
-                                             sqrt_e, pos0, B, E, x, q);
+  launch_pdl(finalize_step_kernel, dim3(B), dim3(64), 0, stream, best, shortlist, forced, step, step_tokens, done, tgt_len,
+             n_done, emb_q, inv_qm, sqrt_e, pos0, B, E, x, q);
 }
 
 void launch_gather_rows(const int8_t* W, const float* pb, const int32_t* c127, const uint32_t* idx, int n_idx, int K,

@@ -191,4 +191,41 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(uint32_t M, uint32_t N) {
   return (2u << 4) | (0u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// Programmatic dependent launch (PDL).  A kernel launched with launch_pdl() may start while its predecessor in the
+// stream is still draining: everything up to pdl_wait() (barrier init, TMEM allocation, descriptor prefetch) overlaps
+// the predecessor's tail; pdl_wait() returns once the predecessor has completed and its writes are visible.  Every
+// thread of a PDL-launched kernel calls pdl_wait() before touching global memory, which also keeps the chain
+// transitive.  pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as soon as resources free up.
+// Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+}  // namespace sb
+
+#include <cstdlib>
+#include <utility>
+namespace sb {
+
+// SLIMT_B200_PDL=0 turns the attribute off (plain stream order) for A/B measurements.
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SLIMT_B200_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 }  // namespace sb

@@ -94,6 +94,8 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
   if (threadIdx.x == 0) SB_TRACE(a, 1);
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_acc = tmem;             // EM blocks x R columns: accumulators of the Wo GEMM, then of FFN2
@@ -352,7 +354,7 @@ int launch(const RowsFfnArgs& a, cudaStream_t stream) {
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  kern<<<tiles < sms ? tiles : sms, kThreads, L::total, stream>>>(a);
+  if (launch_pdl(kern, dim3(tiles < sms ? tiles : sms), dim3(kThreads), L::total, stream, a) != cudaSuccess) return 1;
   return 0;
 }
 
