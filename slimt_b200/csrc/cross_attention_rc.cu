@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
 
   if (warp == 0) {
     // ===== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(w_full, 128 * 1024);
       for (int kb = 0; kb < 2; kb++)
         for (int half = 0; half < 2; half++) {
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
     }
   } else if (warp == 1) {
     // ===== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_k = make_idesc_i8(128, 256);     // A = u8 key rows, B = s8 Wk
       constexpr uint32_t idesc_v = make_idesc_i8_wa(128, 128);  // A = s8 Wv block, B = u8 key rows
       mbar_wait(w_full, 0);

@@ -92,11 +92,15 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
   RingProducer prod{ring, full, empty, 0, L::kStages};
   RingConsumer<kR> cons{ring, full, empty, 0, L::kStages};
 
+  // One leader lane per warp, elected once (elect.sync also tells the compiler the branch is single-threaded, so
+  // descriptors and addresses stay in uniform registers: no per-MMA waterfall loop as with `lane == 0`).  The ring
+  // positions live in the leader's registers across tiles, hence a single election.
+  const bool leader = elect_one();
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, iter++) {
     const int row0 = tile * kR;
     const uint32_t tph = iter & 1;
     if (warp == 0) {
-      if (lane == 0) {
+      if (leader) {
         mbar_expect_tx(x_full, 2 * EK * kOpK);
         for (int kb = 0; kb < EK; kb++) {
           tma_load_2d(opnd_xf + kb * kOpK, &a.map_xf, x_full, kb * 128, row0);
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
           for (int kb = 0; kb < EK; kb++) prod.load(&a.map_wq, kb, mb);
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      if (leader) {
         mbar_wait(x_full, tph);
         SB_TRACE(a, 2);
         for (int mb = 0; mb < EM; mb++)

@@ -109,12 +109,16 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
   cons.timing = a.trace != nullptr;
   long long waited_fq = 0;
 
+  // One leader lane per warp, elected once (elect.sync also tells the compiler the branch is single-threaded, so
+  // descriptors and addresses stay in uniform registers: no per-MMA waterfall loop as with `lane == 0`).  The ring
+  // positions live in the leader's registers across tiles, hence a single election.
+  const bool leader = elect_one();
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, iter++) {
     const int row0 = tile * R;
     const uint32_t tph = iter & 1;
     if (warp == 0) {
       // ===== TMA producer: the tile's input operand, then every weight tile in consumption order
-      if (lane == 0) {
+      if (leader) {
         mbar_expect_tx(a_full, EK * kOpK);
         for (int kb = 0; kb < EK; kb++) tma_load_2d(opnd_a + kb * kOpK, &a.map_a, a_full, kb * 128, row0);
         for (int mb = 0; mb < EM; mb++)
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
       }
     } else if (warp == 1) {
       // ===== MMA issuer
-      if (lane == 0) {
+      if (leader) {
         mbar_wait(a_full, tph);
         SB_TRACE(a, 2);
         for (int mb = 0; mb < EM; mb++)
