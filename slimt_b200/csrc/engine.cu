@@ -294,6 +294,7 @@ int Model::load(Context* c, const void* bin, size_t bytes, int enc_layers, int d
     if (upload(q, static_cast<size_t>(K) * N, reinterpret_cast<void**>(&w.w))) return 1;
     if (upload(pb.data(), 4ul * N, reinterpret_cast<void**>(&w.pb))) return 1;
     if (ctx->make_map(&w.map128, w.w, N, K, 128)) return 1;
+    if (N >= 32 && ctx->make_map(&w.map32, w.w, N, K, 32)) return 1;
     return 0;
   };
   auto ln = [&](const std::string& prefix, DevLN& l) -> int {
@@ -632,6 +633,14 @@ int model_forward(Model& m, ForwardArgs& a) {
   CUtensorMap map_attn_q;  // u8 [R][E], box {128 B, 128 rows}: operand of the encoder's row-tile kernel
   if (c.make_map(&map_attn_q, attn_q, R, E, 128)) return 1;
 
+  // SLIMT_B200_SELFATTN=split keeps the projections and the attention as separate kernels (parity cross-check)
+  const char* sa_env = getenv("SLIMT_B200_SELFATTN");
+  const bool attn_fused = enc_attention_supported(E, H, dh, T) && !(sa_env && strcmp(sa_env, "split") == 0);
+  CUtensorMap map_qa[3];
+  if (attn_fused)
+    for (int i = 0; i < 3; i++)
+      if (c.make_map(&map_qa[i], qa[i], R, E, 128)) return 1;
+
   // ---- embedding (Model.cc:195-197)
   {
     QuantOuts q = qouts();
@@ -645,7 +654,25 @@ int model_forward(Model& m, ForwardArgs& a) {
   // ---- encoder (Transformer.cc:57-69; EncoderLayer::forward Modules.cc:321-334)
   for (int i = 0; i < Le; i++) {
     const EncLayerW& L = m.enc[i];
-    {
+    if (attn_fused) {
+      // q/k/v projections + scaled dot-product attention in one kernel: Q, K, V stay on the SM (enc_attention.cu)
+      EncAttnArgs k{};
+      k.map_aq = map_qa[0], k.map_ak = map_qa[1], k.map_av = map_qa[2];
+      k.map_wq = L.self.q.map32, k.map_wk = L.self.k.map32, k.map_wv = L.self.v.map32;
+      k.pb_q = L.self.q.pb, k.pb_k = L.self.k.pb, k.pb_v = L.self.v.pb;
+      k.um_q = L.self.q.um, k.um_k = L.self.k.um, k.um_v = L.self.v.um;
+      k.lengths = d_lengths, k.B = B, k.T = T;
+      // 1/sqrt(dim_head) evaluated in double then narrowed, as `1.0F / std::sqrt(size_t)` does (Modules.cc:43)
+      k.dk = static_cast<float>(1.0 / std::sqrt(static_cast<double>(dh)));
+      k.out_q = reinterpret_cast<uint8_t*>(attn_q), k.aq_out = L.self.o.aq;
+      const double Rd = R, Ed = E;
+      LaunchScope ls(c, "enc_qkv_attention_fused", 2.0 * Rd * Ed * Ed * 3.0, 4.0 * Rd * Ed + 3.0 * Ed * Ed);
+      if (launch_enc_attention(k, c.num_sms, s)) {
+        set_error("fused encoder attention kernel launch failed");
+        return 1;
+      }
+    } else {
+      {
       GemmCall g(&c, "enc_gemm_qkv_f32", R, E, E, EPI_F32, 3);
       GemmProblem* pq = g.add(qa[0], L.self.q);
       GemmProblem* pk = g.add(qa[1], L.self.k);
@@ -660,6 +687,7 @@ int model_forward(Model& m, ForwardArgs& a) {
       qadd(q, attn_q, L.self.o.aq);
       LaunchScope ls(c, "enc_self_attention", 0, 13.0 * R * E);
       launch_self_attention(Qb, Kb, Vb, d_lengths, B, T, H, dh, nullptr, q, s);
+    }
     }
     if (E == 256 && F == 1536) {
       // Wo + residual + LN, FFN1 + ReLU, FFN2 + residual + LN in one row-tile kernel, 128 rows per CTA

@@ -101,6 +101,7 @@ struct DevWeight {
   float aq = 0, bq = 0, um = 0;
   int8_t* w = nullptr;      // [N][K]
   CUtensorMap map128;       // TMA view of w with box {128 B, 128 rows}: the A operand of the row-tile kernels
+  CUtensorMap map32;        // box {128 B, 32 rows}: one head's features, the B operand of the fused encoder attention
   float* pb = nullptr;      // [N]
   // output layer only: inputs of the fused argmax GEMM's bound filter (gemm_out.cu)
   int32_t* c127 = nullptr;  // [N] 127 * colsum

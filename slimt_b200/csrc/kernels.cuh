@@ -57,6 +57,24 @@ struct CrossRcArgs {
 bool cross_attention_rc_supported(int E, int H, int dh, int S);
 int launch_cross_attention_rc(const CrossRcArgs& a, int num_sms, cudaStream_t stream);
 
+// Encoder self-attention fused with its q/k/v projections (enc_attention.cu): Q, K and V never reach HBM.
+// Bit-identical to launch_gemm_i8(EPI_F32) x 3 followed by launch_self_attention.
+struct EncAttnArgs {
+  CUtensorMap map_aq, map_ak, map_av;  // u8 [B*T][E], box {128 B, 128 rows}: x quantised with Wq's / Wk's / Wv's a_quant
+  CUtensorMap map_wq, map_wk, map_wv;  // s8 [E][E], box {128 B, 32 rows}
+  const float* pb_q;                   // prepared biases
+  const float* pb_k;
+  const float* pb_v;
+  float um_q, um_k, um_v;              // 1 / (a_quant * b_quant)
+  const uint32_t* lengths;
+  int B, T;
+  float dk;                            // 1 / sqrt(head size)
+  uint8_t* out_q;                      // u8 [B*T][E]: Wo's operand
+  float aq_out;
+};
+bool enc_attention_supported(int E, int H, int dh, int T);
+int launch_enc_attention(const EncAttnArgs& a, int num_sms, cudaStream_t stream);
+
 // SSRU cell tail (slimt/Modules.cc:190-235): c = highway(c_prev, Wx, f); h = LN(x + relu(c)); state <- c.
 void launch_ssru_ln(const float* f, const float* wx, float* state, const float* x, const float* ln_scale,
                     const float* ln_bias, float eps, int B, int E, float* h, QuantOuts q, cudaStream_t stream);

@@ -89,6 +89,29 @@ def test_cross_attention_recompute_equals_cached_path(tiny_gpu, shape, monkeypat
     assert np.array_equal(rc["logits"], cached["logits"])
 
 
+@pytest.mark.parametrize("shape", [(37, 32), (9, 20), (70, 5), (130, 1), (5, 33), (7, 64), (40, 48), (3, 2)])
+def test_fused_encoder_attention_equals_split_path(tiny_gpu, shape, monkeypatch):
+    """T <= 64 batches run the q/k/v projections and the self-attention as one kernel (enc_attention.cu): tiles of
+    floor(128 / T) whole sentences, sentences straddling warps, ragged lengths.  Forcing the split path (three GEMMs
+    writing f32 Q, K, V + self_attention_kernel) must give the same bits, and both must equal the oracle."""
+    m, orc = tiny_gpu
+    B, T = shape
+    sents = synth.make_sentences(B, (1, T), seed=11 * B + T)
+    sents[0] = synth.make_sentences(1, T, seed=2)[0]
+    sents[-1] = synth.make_sentences(1, T, seed=3)[0]
+    tokens, lengths = util.pad_batch(sents)
+    ref = orc.forward(tokens, lengths, keep=True)
+    fused = m.forward(tokens, lengths, want_encoder=True, want_logits=True)
+    monkeypatch.setenv("SLIMT_B200_SELFATTN", "split")
+    split = m.forward(tokens, lengths, want_encoder=True, want_logits=True)
+    monkeypatch.delenv("SLIMT_B200_SELFATTN")
+    _compare(split, ref, lengths, T)
+    _compare(fused, ref, lengths, T)
+    valid = np.arange(T)[None, :] < np.asarray(lengths)[:, None]
+    assert np.array_equal(fused["encoder_out"][valid], split["encoder_out"][valid])
+    assert np.array_equal(fused["logits"], split["logits"])
+
+
 def test_forward_with_shortlist(tiny_gpu, shortlist_assets):
     m, orc = tiny_gpu
     fr, offs, lists = shortlist_assets[1]
