@@ -45,7 +45,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__cycles_active.avg", "sm__cycles_active.max", "sm__cycles_elapsed.avg"]
 TAGS = {"cross_attention_kernel": "dec_cross_attention", "out_argmax_kernel": "dec_gemm_out_argmax", "dec_ssru_kernel": "dec_ssru_q_fused",
-        "self_attention_kernel": "enc_self_attention"}
+        "self_attention_kernel": "enc_self_attention",
+        "cross_attention_rc_kernel": "dec_cross_attention_rc", "enc_attention_kernel": "enc_qkv_attention_fused"}
 traffic = {}
 tpath = os.path.join(out_dir, "roofline_traffic.json")
 if os.path.exists(tpath):
