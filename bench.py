@@ -177,6 +177,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     dist = None
+    # stdout carries exactly one JSON line: native libraries that write to fd 1 (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -364,7 +368,7 @@ def main():
             dt = time.perf_counter() - t0
             out["cpu_baseline"] = {"value": sum(len(s) for s in res["sentences"]) / dt, "unit": "tokens/s", "cores": 1,
                                    "kind": "port", "sample": "16 sentences x 32 tokens through oracle/slimt_oracle.py"}
-    print(json.dumps(out))
+    os.write(json_fd, (json.dumps(out) + "\n").encode())
     return 0
 
 
