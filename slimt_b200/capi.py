@@ -13,7 +13,8 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libslimt_b200.so")
+# SLIMT_B200_LIB selects another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("SLIMT_B200_LIB") or os.path.join(_HERE, "libslimt_b200.so")
 _lib = None
 
 EXPORTS = [

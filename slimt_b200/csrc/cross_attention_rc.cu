@@ -95,6 +95,16 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
   __syncthreads();
   tc_fence_after();
   pdl_launch_dependents();
+  // Wk and Wv never change: request them before waiting for the preceding kernel, so that the 128 KB arrive while
+  // it drains.
+  if (SB_PRE_CROSS && warp == 0 && elect_one()) {
+    mbar_expect_tx(w_full, 128 * 1024);
+    for (int kb = 0; kb < 2; kb++)
+      for (int half = 0; half < 2; half++) {
+        tma_load_2d(s_wk + kb * 32768 + half * 16384, &a.map_wk, w_full, kb * 128, half * 128);
+        tma_load_2d(s_wv + kb * 32768 + half * 16384, &a.map_wv, w_full, kb * 128, half * 128);
+      }
+  }
   pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_k = tmem;         // 256 columns: features
@@ -105,12 +115,14 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
   if (warp == 0) {
     // ===== TMA producer
     if (elect_one()) {
-      mbar_expect_tx(w_full, 128 * 1024);
-      for (int kb = 0; kb < 2; kb++)
-        for (int half = 0; half < 2; half++) {
-          tma_load_2d(s_wk + kb * 32768 + half * 16384, &a.map_wk, w_full, kb * 128, half * 128);
-          tma_load_2d(s_wv + kb * 32768 + half * 16384, &a.map_wv, w_full, kb * 128, half * 128);
-        }
+      if (!SB_PRE_CROSS) {
+        mbar_expect_tx(w_full, 128 * 1024);
+        for (int kb = 0; kb < 2; kb++)
+          for (int half = 0; half < 2; half++) {
+            tma_load_2d(s_wk + kb * 32768 + half * 16384, &a.map_wk, w_full, kb * 128, half * 128);
+            tma_load_2d(s_wv + kb * 32768 + half * 16384, &a.map_wv, w_full, kb * 128, half * 128);
+          }
+      }
       uint32_t it = 0;
       for (int g = blockIdx.x; g < n_groups; g += gridDim.x, it++) {
         const uint32_t ph = it & 1;

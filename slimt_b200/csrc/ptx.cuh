@@ -197,6 +197,22 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(uint32_t M, uint32_t N) {
 // thread of a PDL-launched kernel calls pdl_wait() before touching global memory, which also keeps the chain
 // transitive.  pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as soon as resources free up.
 // Both are no-ops for ordinary launches.
+// SB_PREWAIT_LOADS: request constant data (weights) before griddepcontrol.wait.  Build-time switch for A/B runs.
+#ifndef SB_PREWAIT_LOADS
+#define SB_PREWAIT_LOADS 0
+#endif
+#ifndef SB_PRE_SSRU
+#define SB_PRE_SSRU SB_PREWAIT_LOADS
+#endif
+#ifndef SB_PRE_FFN
+#define SB_PRE_FFN SB_PREWAIT_LOADS
+#endif
+#ifndef SB_PRE_OUT
+#define SB_PRE_OUT SB_PREWAIT_LOADS
+#endif
+#ifndef SB_PRE_CROSS
+#define SB_PRE_CROSS SB_PREWAIT_LOADS
+#endif
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

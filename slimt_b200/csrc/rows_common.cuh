@@ -21,7 +21,7 @@ namespace rows {
 constexpr int kWTile = 128 * 128;     // one weight tile: 128 features x 128-byte k-block
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = 128 + kEpiThreads;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-19 epilogue
+constexpr int kThreads = 128 + kEpiThreads;  // warp0 TMA, warps 1 and 3 MMA issuers, warp2 TMEM alloc, warps 4-19 epilogue
 
 // byte offset of element (row r, k index kk) inside a K-major 128B-swizzled operand made of [R x 128 B] k-blocks
 template <int R>

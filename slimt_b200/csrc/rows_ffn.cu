@@ -24,7 +24,10 @@ template <int E, int F, int R>
 struct FfnPlan {
   static constexpr int EK = E / 128, EM = E / 128, FM = F / 128;
   static constexpr int kOpK = R * 128;                                    // one operand k-block
-  static constexpr int kStages = (R == 32) ? ((E == 256) ? 6 : 4) : 3;     // weight ring depth
+  // two weight rings, one per MMA-issuing thread: ring A streams Wo and W1, ring B streams W2
+  static constexpr int kStagesA = (R == 32) ? ((E == 256) ? 4 : 2) : 2;
+  static constexpr int kStagesB = (R == 32) ? ((E == 256) ? 4 : 2) : 2;
+  static constexpr int kStages = kStagesA + kStagesB;
   static constexpr int kTS = (R == 32) ? 8 : 2;                            // TMEM slots for FFN1 blocks
   static constexpr int kFS = (R == 32) ? FM : 4;                           // operand ring slots for relu(W1 y) blocks
   static constexpr bool kParkY = (R != 32);                                // y parked in global (xs aliases the f ring)
@@ -39,11 +42,13 @@ struct FfnPlan {
   static constexpr int after = kParkY ? opnd_f + (xs_bytes > f_bytes ? xs_bytes : f_bytes) : xs + xs_bytes;
   static constexpr int stats = (after + 15) & ~15;                         // mean[R], sigma[R]
   static constexpr int bars = stats + 2 * R * 4;
-  // full[kStages] empty[kStages] a_full g0_done yq_ready g2_done slot_full[kTS] slot_empty[kTS] fq_full[kFS] fq_free[kFS]
+  // full[kStages] empty[kStages] (ring A's stages first) a_full g0_done yq_ready g2_done slot_full[kTS] slot_empty[kTS]
+  // fq_full[kFS] fq_free[kFS]
   static constexpr int n_bars = 2 * kStages + 4 + 2 * kTS + 2 * kFS;
   static constexpr int tmem_slot = bars + n_bars * 8;
   static constexpr int total = tmem_slot + 16 + 1024;
   static_assert(EM * R + kTS * R <= 512, "TMEM columns");
+  static_assert(total <= 227 * 1024, "shared memory");
 };
 
 template <int E, int F, int R>
@@ -95,8 +100,6 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   pdl_launch_dependents();
-  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
-  if (threadIdx.x == 0) SB_TRACE(a, 1);
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_acc = tmem;             // EM blocks x R columns: accumulators of the Wo GEMM, then of FFN2
   const uint32_t tmem_ring = tmem + EM * R;   // kTS slots x R columns: FFN1 feature blocks
@@ -104,8 +107,12 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
   const int n_tiles = (a.M + R - 1) / R;
   uint32_t iter = 0;     // tile iterations of this CTA (phase of the once-per-tile barriers)
   uint32_t blocks = 0;   // FFN1 feature blocks so far: position in the TMEM slot ring and the operand ring (per role)
-  RingProducer prod{ring, full, empty, 0, L::kStages};
-  RingConsumer<R> cons{ring, full, empty, 0, L::kStages};
+  // Ring A feeds warp 1 (Wo, W1), ring B feeds warp 3 (W2); each consumer object lives in its own warp's leader.
+  uint8_t* ring_b = ring + L::kStagesA * kWTile;
+  RingProducer prod_a{ring, full, empty, 0, L::kStagesA};
+  RingProducer prod_b{ring_b, full + L::kStagesA, empty + L::kStagesA, 0, L::kStagesB};
+  RingConsumer<R> cons = (warp == 3) ? RingConsumer<R>{ring_b, full + L::kStagesA, empty + L::kStagesA, 0, L::kStagesB}
+                                     : RingConsumer<R>{ring, full, empty, 0, L::kStagesA};
   cons.timing = a.trace != nullptr;
   long long waited_fq = 0;
 
@@ -113,25 +120,43 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
   // descriptors and addresses stay in uniform registers: no per-MMA waterfall loop as with `lane == 0`).  The ring
   // positions live in the leader's registers across tiles, hence a single election.
   const bool leader = elect_one();
+  // The weight stream of one tile in consumption order; tiles [from_a, to_a) of ring A's sequence and [from_b, to_b)
+  // of ring B's are requested, the others stepped over.
+  auto load_weights = [&](int from_a, int from_b, int to_a, int to_b) {
+    int ia = 0, ib = 0;
+    for (int mb = 0; mb < EM; mb++)
+      for (int kb = 0; kb < EK; kb++, ia++)
+        if (ia >= from_a && ia < to_a) prod_a.load(&a.map_wo, kb, mb);
+    for (int st = 0; st < FM + kLook; st++) {
+      if (st < FM)
+        for (int kb = 0; kb < EK; kb++, ia++)
+          if (ia >= from_a && ia < to_a) prod_a.load(&a.map_w1, kb, st);
+      if (st >= kLook)
+        for (int mb = 0; mb < EM; mb++, ib++)
+          if (ib >= from_b && ib < to_b) prod_b.load(&a.map_w2, st - kLook, mb);
+    }
+  };
+  // Weights are never written by a kernel, so the first ring-fuls are requested before waiting for the preceding
+  // kernel: their L2 latency hides behind its tail.
+  const int pre_a = L::kStagesA, pre_b = L::kStagesB;
+  if (SB_PRE_FFN && warp == 0 && leader && static_cast<int>(blockIdx.x) < n_tiles) load_weights(0, 0, pre_a, pre_b);
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
+  if (threadIdx.x == 0) SB_TRACE(a, 1);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, iter++) {
     const int row0 = tile * R;
     const uint32_t tph = iter & 1;
     if (warp == 0) {
-      // ===== TMA producer: the tile's input operand, then every weight tile in consumption order
+      // ===== TMA producer: the tile's input operand, then every weight tile in consumption order.  The weight
+      // tiles that fit the rings at kernel start were already requested before griddepcontrol.wait (above).
       if (leader) {
         mbar_expect_tx(a_full, EK * kOpK);
         for (int kb = 0; kb < EK; kb++) tma_load_2d(opnd_a + kb * kOpK, &a.map_a, a_full, kb * 128, row0);
-        for (int mb = 0; mb < EM; mb++)
-          for (int kb = 0; kb < EK; kb++) prod.load(&a.map_wo, kb, mb);
-        for (int st = 0; st < FM + kLook; st++) {
-          if (st < FM)
-            for (int kb = 0; kb < EK; kb++) prod.load(&a.map_w1, kb, st);
-          if (st >= kLook)
-            for (int mb = 0; mb < EM; mb++) prod.load(&a.map_w2, st - kLook, mb);
-        }
+        load_weights(iter == 0 && SB_PRE_FFN ? pre_a : 0, iter == 0 && SB_PRE_FFN ? pre_b : 0, 1 << 30, 1 << 30);
       }
     } else if (warp == 1) {
-      // ===== MMA issuer
+      // ===== MMA issuer A: the Wo GEMM and the FFN1 feature blocks.  The FFN2 k-steps are issued by warp 3, so that
+      // neither stream waits behind the other's barrier / fence / commit latencies (a single issuing thread needed
+      // ~2200 cycles per block for ~700 cycles of tensor-pipe work).  Each has its own weight ring.
       if (leader) {
         mbar_wait(a_full, tph);
         SB_TRACE(a, 2);
@@ -155,7 +180,17 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
             umma_commit(&slot_full[s]);
             if (st < 12) SB_TRACE(a, 16 + st);
           }
-          if (st >= kLook) {  // FFN2 k-step kb2 = st - kLook, fed by the requantised block kb2
+        }
+        if (a.trace)  // slot 14: cycles this thread spent waiting for weight tiles
+          a.trace[blockIdx.x * kTraceSlots + 14] = a.trace[blockIdx.x * kTraceSlots] + cons.waited;
+        blocks += FM;
+      }
+    } else if (warp == 3) {
+      // ===== MMA issuer B: FFN2 k-step kb2 = st - kLook, fed by the requantised block kb2.  Its first MMA overwrites
+      // the Wo accumulators: fq_full of block 0 is only reached after every epilogue warp has drained them.
+      if (leader) {
+        for (int st = kLook; st < FM + kLook; st++) {
+          {
             const int kb2 = st - kLook;
             const uint32_t n = blocks + kb2;
             const uint32_t s = n % L::kFS, ph = (n / L::kFS) & 1;
@@ -172,10 +207,8 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
           }
         }
         umma_commit(g2_done);
-        if (a.trace) {  // slots 14, 15: cycles the MMA thread spent waiting for weight tiles / requantised blocks
-          a.trace[blockIdx.x * kTraceSlots + 14] = a.trace[blockIdx.x * kTraceSlots] + cons.waited;
+        if (a.trace)  // slot 15: cycles this thread spent waiting for requantised blocks
           a.trace[blockIdx.x * kTraceSlots + 15] = a.trace[blockIdx.x * kTraceSlots] + waited_fq;
-        }
         blocks += FM;
       }
     } else if (warp >= 4) {
