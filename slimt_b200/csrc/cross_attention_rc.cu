@@ -238,32 +238,46 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(k_drained);
+        // the two heads' fma chains advance together (source order is what the in-order issue sees)
         float sc[2];
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-          const float* qh = s_q + j * kE + (h0 + hh) * kDH;
-          const float* pbh = s_pbk + (h0 + hh) * kDH;
-          float acc = 0.0f;
+        {
+          const float* qh = s_q + j * kE + h0 * kDH;
+          const float* pbh = s_pbk + h0 * kDH;
+          float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll
           for (int d = 0; d < kDH; d += 4) {
-            const float4 qq = *reinterpret_cast<const float4*>(qh + d);
-            const float4 pb = *reinterpret_cast<const float4*>(pbh + d);
-            const uint32_t* vv = hh == 0 ? v0 : v1;
-            acc = fmaf(qq.x, dequant1(static_cast<int>(vv[d]), a.um_k, pb.x), acc);
-            acc = fmaf(qq.y, dequant1(static_cast<int>(vv[d + 1]), a.um_k, pb.y), acc);
-            acc = fmaf(qq.z, dequant1(static_cast<int>(vv[d + 2]), a.um_k, pb.z), acc);
-            acc = fmaf(qq.w, dequant1(static_cast<int>(vv[d + 3]), a.um_k, pb.w), acc);
+            const float4 q0 = *reinterpret_cast<const float4*>(qh + d);
+            const float4 q1 = *reinterpret_cast<const float4*>(qh + kDH + d);
+            const float4 p0 = *reinterpret_cast<const float4*>(pbh + d);
+            const float4 p1 = *reinterpret_cast<const float4*>(pbh + kDH + d);
+            acc0 = fmaf(q0.x, dequant1(static_cast<int>(v0[d]), a.um_k, p0.x), acc0);
+            acc1 = fmaf(q1.x, dequant1(static_cast<int>(v1[d]), a.um_k, p1.x), acc1);
+            acc0 = fmaf(q0.y, dequant1(static_cast<int>(v0[d + 1]), a.um_k, p0.y), acc0);
+            acc1 = fmaf(q1.y, dequant1(static_cast<int>(v1[d + 1]), a.um_k, p1.y), acc1);
+            acc0 = fmaf(q0.z, dequant1(static_cast<int>(v0[d + 2]), a.um_k, p0.z), acc0);
+            acc1 = fmaf(q1.z, dequant1(static_cast<int>(v1[d + 2]), a.um_k, p1.z), acc1);
+            acc0 = fmaf(q0.w, dequant1(static_cast<int>(v0[d + 3]), a.um_k, p0.w), acc0);
+            acc1 = fmaf(q1.w, dequant1(static_cast<int>(v1[d + 3]), a.um_k, p1.w), acc1);
           }
-          sc[hh] = __fmul_rn(a.dk, acc);
+          sc[0] = __fmul_rn(a.dk, acc0);
+          sc[1] = __fmul_rn(a.dk, acc1);
         }
-        // softmax over the sentence's keys (slimt/TensorOps.cc:282-315): max, exp, sum in key order, divide
+        // softmax over the sentence's keys (slimt/TensorOps.cc:282-315): max, exp, sum in key order, divide.  Both
+        // heads advance together: nothing is stored between the two expf evaluations (a store would pin the second
+        // one's table load behind it), so their double-precision chains interleave.
         float mx[2], e[2], sum[2];
 #pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-          mx[hh] = valid ? sc[hh] : -3.402823466e+38f;
+        for (int hh = 0; hh < 2; hh++) mx[hh] = valid ? sc[hh] : -3.402823466e+38f;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], o));
-          e[hh] = valid ? expf_glibc_nonpos_tab(__fsub_rn(sc[hh], mx[hh]), exp_tab) : 0.0f;
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int hh = 0; hh < 2; hh++) mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], o));
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) e[hh] = expf_glibc_nonpos_tab(__fsub_rn(sc[hh], mx[hh]), exp_tab);
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          e[hh] = valid ? e[hh] : 0.0f;
           s_p[(j * kH + h0 + hh) * kKeys + lane] = e[hh];
           sum[hh] = 0.0f;
         }
@@ -302,34 +316,48 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(v_drained);
+        auto emit = [&](int b, float acc) {
+          const size_t off = static_cast<size_t>(b) * kE + v_feat;
+          if (a.out_f32) a.out_f32[off] = acc;
+          for (int k = 0; k < a.qo.n; k++) a.qo.ptr[k][off] = static_cast<int8_t>(quantize1(acc, a.qo.aq[k]));
+        };
+        if (len_v[0] == kKeys && len_v[1] == kKeys && b0 + j0 + 1 < a.B) {
+          // both sentences full: their two chains advance together
+          const float* pr0 = s_p + (j0 * kH + v_head) * kKeys;
+          const float* pr1 = pr0 + kH * kKeys;
+          float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll
-        for (int jj = 0; jj < 2; jj++) {
-          const int j = j0 + jj;
-          const int b = b0 + j;
-          if (b >= a.B) continue;
-          const int len = len_v[jj];
-          const float* pr = s_p + (j * kH + v_head) * kKeys;
-          const uint32_t* vv = jj == 0 ? v0 : v1;
-          float acc = 0.0f;
-          if (len == kKeys) {
+          for (int l = 0; l < kKeys; l += 4) {
+            const float4 p0 = *reinterpret_cast<const float4*>(pr0 + l);
+            const float4 p1 = *reinterpret_cast<const float4*>(pr1 + l);
+            acc0 = fmaf(p0.x, dequant1(static_cast<int>(v0[l]), a.um_v, pbv), acc0);
+            acc1 = fmaf(p1.x, dequant1(static_cast<int>(v1[l]), a.um_v, pbv), acc1);
+            acc0 = fmaf(p0.y, dequant1(static_cast<int>(v0[l + 1]), a.um_v, pbv), acc0);
+            acc1 = fmaf(p1.y, dequant1(static_cast<int>(v1[l + 1]), a.um_v, pbv), acc1);
+            acc0 = fmaf(p0.z, dequant1(static_cast<int>(v0[l + 2]), a.um_v, pbv), acc0);
+            acc1 = fmaf(p1.z, dequant1(static_cast<int>(v1[l + 2]), a.um_v, pbv), acc1);
+            acc0 = fmaf(p0.w, dequant1(static_cast<int>(v0[l + 3]), a.um_v, pbv), acc0);
+            acc1 = fmaf(p1.w, dequant1(static_cast<int>(v1[l + 3]), a.um_v, pbv), acc1);
+          }
+          emit(b0 + j0, acc0);
+          emit(b0 + j0 + 1, acc1);
+        } else {
 #pragma unroll
-            for (int l = 0; l < kKeys; l += 4) {
-              const float4 p = *reinterpret_cast<const float4*>(pr + l);
-              acc = fmaf(p.x, dequant1(static_cast<int>(vv[l]), a.um_v, pbv), acc);
-              acc = fmaf(p.y, dequant1(static_cast<int>(vv[l + 1]), a.um_v, pbv), acc);
-              acc = fmaf(p.z, dequant1(static_cast<int>(vv[l + 2]), a.um_v, pbv), acc);
-              acc = fmaf(p.w, dequant1(static_cast<int>(vv[l + 3]), a.um_v, pbv), acc);
-            }
-          } else {
+          for (int jj = 0; jj < 2; jj++) {
+            const int j = j0 + jj;
+            const int b = b0 + j;
+            if (b >= a.B) continue;
             // ragged sentence: only its own keys take part (the rows beyond belong to the next sentence)
+            const int len = len_v[jj];
+            const float* pr = s_p + (j * kH + v_head) * kKeys;
+            const uint32_t* vv = jj == 0 ? v0 : v1;
+            float acc = 0.0f;
 #pragma unroll
             for (int l = 0; l < kKeys; l++) {
               if (l < len) acc = fmaf(pr[l], dequant1(static_cast<int>(vv[l]), a.um_v, pbv), acc);
             }
+            emit(b, acc);
           }
-          const size_t off = static_cast<size_t>(b) * kE + v_feat;
-          if (a.out_f32) a.out_f32[off] = acc;
-          for (int k = 0; k < a.qo.n; k++) a.qo.ptr[k][off] = static_cast<int8_t>(quantize1(acc, a.qo.aq[k]));
         }
       }
     }
