@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kOutThreads, 1)
       dm1_next = ch + 1 < nch ? __ldg(dmax + ch + 1) : ninf;
     };
     // exact logits of one 32-column chunk held in v[]; returns the chunk maximum and its first column
-    auto exact_chunk = [&](const uint32_t (&v)[32], int nb, float& mx, int& idx) {
+    auto exact_chunk = [&](const uint32_t (&v)[32], int nb, float floor_v, float& mx, int& idx) {
       float y[32];
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -203,10 +203,16 @@ __global__ void __launch_bounds__(kOutThreads, 1)
 #pragma unroll
       for (int j = 0; j < 8; j++) t8[j] = fmaxf(fmaxf(y[4 * j], y[4 * j + 1]), fmaxf(y[4 * j + 2], y[4 * j + 3]));
       mx = fmaxf(fmaxf(fmaxf(t8[0], t8[1]), fmaxf(t8[2], t8[3])), fmaxf(fmaxf(t8[4], t8[5]), fmaxf(t8[6], t8[7])));
-      // first column of the chunk that attains the maximum (greedy_sample keeps the first strict max)
+      // first column of the chunk that attains the maximum (greedy_sample keeps the first strict max).  The chunk is
+      // evaluated whenever ANY row of the warp passes the bound filter (lane = row: every row has its own best so
+      // far, measured ~54 % of warp-chunks), but its maximum only matters for a row it can raise: the 62-instruction
+      // search is skipped unless some lane's exact maximum reaches that lane's floor.  A lane whose maximum stays
+      // below its floor keeps idx = 31; its candidate then packs to a key below the stored best and is never written.
       idx = 31;
+      if (__any_sync(0xffffffffu, mx >= floor_v)) {
 #pragma unroll
-      for (int j = 30; j >= 0; j--) idx = (y[j] == mx) ? j : idx;
+        for (int j = 30; j >= 0; j--) idx = (y[j] == mx) ? j : idx;
+      }
     };
     auto int_max32 = [](const uint32_t (&v)[32]) {
       int vt[8];
@@ -250,7 +256,7 @@ __global__ void __launch_bounds__(kOutThreads, 1)
       if (__any_sync(0xffffffffu, ub0 >= thr && nb0 < N)) {
         float mx;
         int idx;
-        exact_chunk(v0, nb0, mx, idx);
+        exact_chunk(v0, nb0, thr, mx, idx);
         if (nb0 < N && ub0 >= thr) {
           bv = mx, bi = static_cast<uint32_t>(nb0 + idx), have = true;
           thr = fmaxf(thr, mx);
@@ -259,7 +265,7 @@ __global__ void __launch_bounds__(kOutThreads, 1)
       if (__any_sync(0xffffffffu, ub1 >= thr && nb0 + 32 < N)) {
         float mx;
         int idx;
-        exact_chunk(v1, nb0 + 32, mx, idx);
+        exact_chunk(v1, nb0 + 32, thr, mx, idx);
         if (nb0 + 32 < N && ub1 >= thr && (!have || mx > bv)) {
           bv = mx, bi = static_cast<uint32_t>(nb0 + 32 + idx), have = true;
         }
