@@ -37,6 +37,30 @@ SENTENCES_PER_GPU = 4096
 SRC_LEN = 32
 LIMIT = 1.5
 MODEL_SEED = 1234
+
+# --workload: the headline (default) is BASELINE.json configs[1]; the others are the remaining GPU configs of
+# BASELINE.json, benchmarked with the same harness (they are parity-test cases first: tests/test_gpu_model.py).
+WORKLOADS = {
+    "tiny_shortlist": dict(dims="TINY", shortlist=True, sentences=4096, length=32, max_words=4096 * 32,
+                           desc="tiny11 int8 (emb 256, ffn 1536, 6 enc / 2 SSRU dec, vocab 32000, random-init seed 1234) "
+                                "with lexical shortlist, greedy decode of 4096 synthetic sentences x 32 tokens per GPU "
+                                "(BASELINE.json configs[1])"),
+    "tiny_full": dict(dims="TINY", shortlist=False, sentences=4096, length=32, max_words=4096 * 32,
+                      desc="tiny11 int8 without shortlist (full 32000-column output GEMM + fused argmax), 4096 synthetic "
+                           "sentences x 32 tokens per GPU (BASELINE.json configs[3])"),
+    "base_shortlist": dict(dims="BASE", shortlist=True, sentences=4096, length=32, max_words=4096 * 32,
+                           desc="base int8 (emb 512, ffn 2048, 6 enc / 2 SSRU dec, vocab 32000, random-init) with lexical "
+                                "shortlist, 4096 synthetic sentences x 32 tokens per GPU (BASELINE.json configs[2])"),
+    "mixed": dict(dims="TINY", shortlist=True, sentences=16384, length=(8, 256), max_words=1 << 20,
+                  desc="tiny11 int8 with lexical shortlist, mixed-length sweep: 16384 synthetic sentences per GPU per step, "
+                       "lengths U{8..256}, length-bucketed by the Batcher into batches of <= 1048576 padded words "
+                       "(BASELINE.json configs[4], per-step slice of the 1M-sentence sweep)"),
+}
+WL = WORKLOADS["tiny_shortlist"]
+
+
+def wl_dims():
+    return getattr(synth, WL["dims"])
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "slimt_ref")
 
 
@@ -90,12 +114,13 @@ class ClockSampler:
 
 
 def build_assets(tmp: str, rank: int):
-    model_path = os.path.join(tmp, "tiny11.bin")
-    synth.write_model(model_path, synth.make_params(synth.TINY, seed=MODEL_SEED))
-    fr, offs, lists = synth.make_shortlist(vocab=synth.TINY.vocab, frequent=100, best=100, seed=7)
+    dims = wl_dims()
+    model_path = os.path.join(tmp, "model.bin")
+    synth.write_model(model_path, synth.make_params(dims, seed=MODEL_SEED))
+    fr, offs, lists = synth.make_shortlist(vocab=dims.vocab, frequent=100, best=100, seed=7)
     sl_path = os.path.join(tmp, "lex.s2t.bin")
     synth.write_shortlist(sl_path, fr, offs, lists, best=100)
-    sentences = synth.make_sentences(SENTENCES_PER_GPU, SRC_LEN, vocab=synth.TINY.vocab, seed=1000 + rank)
+    sentences = synth.make_sentences(WL["sentences"], WL["length"], vocab=dims.vocab, seed=1000 + rank)
     return model_path, sl_path, (fr, offs, lists), sentences
 
 
@@ -108,7 +133,7 @@ def cpu_reference_run(model_path, shortlist, sentences, workers, batch_sentences
     for b in range(nb):
         chunk = sentences[b * batch_sentences:(b + 1) * batch_sentences]
         words = np.concatenate(chunk)
-        sl = so.shortlist_generate(words, fr, offs, lists, synth.TINY.vocab)
+        sl = so.shortlist_generate(words, fr, offs, lists, wl_dims().vocab) if WL["shortlist"] else None
         recs.append(synth.pack_batch(chunk, LIMIT, sl))
     with tempfile.NamedTemporaryFile(suffix=".batches", delete=False) as f:
         f.write(np.uint32(len(recs)).tobytes() + b"".join(recs))
@@ -139,7 +164,7 @@ def run_reference_arm(args):
     secs = sum(l["seconds"] for l in timed)
     toks = sum(l["target_tokens"] for l in timed)
     value = toks / secs
-    sample_desc = f"{len(sample)} of {SENTENCES_PER_GPU} sentences x {SRC_LEN} tokens per step, 64-sentence batches, one per thread"
+    sample_desc = f"{len(sample)} of {WL['sentences']} sentences (lengths {WL['length']}) per step, 64-sentence batches, one per thread"
     print(json.dumps({
         "impl": "reference", "metric": "target_tokens_per_sec", "value": value, "unit": "tokens/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(timed)),
@@ -152,11 +177,8 @@ def run_reference_arm(args):
 
 
 def workload_config():
-    return {"workload": "tiny11 int8 (emb 256, ffn 1536, 6 enc / 2 SSRU dec, vocab 32000, random-init seed 1234) "
-                        "with lexical shortlist, greedy decode of 4096 synthetic sentences x 32 tokens per GPU "
-                        "(BASELINE.json configs[1])",
-            "sentences_per_gpu": SENTENCES_PER_GPU, "src_len": SRC_LEN, "limit_factor": LIMIT,
-            "max_words": SENTENCES_PER_GPU * SRC_LEN, "l2": "flushed between timed steps (256 MiB memset)",
+    return {"workload": WL["desc"], "sentences_per_gpu": WL["sentences"], "src_len": WL["length"], "limit_factor": LIMIT,
+            "max_words": WL["max_words"], "l2": "flushed between timed steps (256 MiB memset)",
             "sharding": "independent sentences per rank, no collective"}
 
 
@@ -167,9 +189,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="tiny_shortlist", choices=sorted(WORKLOADS),
+                    help="tiny_shortlist = the headline (BASELINE.json configs[1]); the others are its remaining GPU configs")
     ap.add_argument("--profiler-range", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
+    global WL
+    WL = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -192,8 +218,8 @@ def main():
     tmp = tempfile.mkdtemp(prefix=f"slimt_b200_bench_{rank}_")
     model_path, sl_path, shortlist, sentences = build_assets(tmp, rank)
     model = capi.Model(ctx, open(model_path, "rb").read())
-    sl_bin = open(sl_path, "rb").read()
-    max_words = SENTENCES_PER_GPU * SRC_LEN
+    sl_bin = open(sl_path, "rb").read() if WL["shortlist"] else None
+    max_words = WL["max_words"]
 
     # ---- device-resident arm: the batches a Batcher would form, uploaded once
     plan = capi.batcher_plan([len(s) for s in sentences], max_words)
@@ -205,10 +231,13 @@ def main():
         for r, i in enumerate(ids):
             tok[r, :len(sentences[i])] = sentences[i]
             lens[r] = len(sentences[i])
-        sl = capi.shortlist_generate(sl_bin, np.concatenate([sentences[i] for i in ids]), model.V)
         max_steps = int(np.float32(LIMIT) * np.float32(width))
-        resident.append({"B": B, "T": width, "tok": ctx.to_device(tok), "lens": ctx.to_device(lens),
-                         "sl": ctx.to_device(sl), "nsl": len(sl), "steps": ctx.dev_alloc(4 * max_steps * B)})
+        entry = {"B": B, "T": width, "tok": ctx.to_device(tok), "lens": ctx.to_device(lens), "sl": None, "nsl": 0,
+                 "steps": ctx.dev_alloc(4 * max_steps * B)}
+        if sl_bin is not None:
+            sl = capi.shortlist_generate(sl_bin, np.concatenate([sentences[i] for i in ids]), model.V)
+            entry["sl"], entry["nsl"] = ctx.to_device(sl), len(sl)
+        resident.append(entry)
 
     def resident_pass():
         toks = 0
@@ -251,9 +280,9 @@ def main():
     h_offsets = np.zeros(len(sentences) + 1, dtype=np.uint64)
     h_offsets[1:] = np.cumsum([len(s) for s in sentences])
     h_tokens = np.concatenate([np.asarray(s, dtype=np.uint32) for s in sentences])
-    h_out_tokens = np.zeros(len(sentences) * (int(LIMIT * SRC_LEN) + 1), dtype=np.uint32)
+    h_out_tokens = np.zeros(len(sentences) * (int(LIMIT * max(len(s) for s in sentences)) + 1), dtype=np.uint32)
     h_out_offsets = np.zeros(len(sentences) + 1, dtype=np.uint64)
-    sl_buf = (ctypes.c_char * len(sl_bin)).from_buffer_copy(sl_bin)
+    sl_buf = (ctypes.c_char * len(sl_bin)).from_buffer_copy(sl_bin) if sl_bin is not None else None
     for _ in range(max(1, args.warmup - 1)):
         model.translate_flat(h_tokens, h_offsets, max_words, LIMIT, sl_buf, h_out_tokens, h_out_offsets)
     barrier()
@@ -345,14 +374,14 @@ def main():
         "batches_per_step": len(resident),
     }
 
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and args.workload in ("tiny_shortlist", "tiny_full"):
         cores = os.cpu_count() or 1
         if os.path.exists(REF_BIN):
             sample = sentences[:64 * cores]
             lines = cpu_reference_run(model_path, shortlist, sample, cores, repeats=2)
             best = max(l["target_tokens_per_s"] for l in lines)
             out["cpu_baseline"] = {"value": best, "unit": "tokens/s", "cores": cores, "kind": "reference",
-                                   "sample": f"{len(sample)} of {SENTENCES_PER_GPU} sentences x {SRC_LEN} tokens, 64-sentence "
+                                   "sample": f"{len(sample)} of {WL['sentences']} sentences x {SRC_LEN} tokens, 64-sentence "
                                              f"batches, one per host thread (intgemm provider, ruy sgemm), best of 2"}
         else:
             from oracle import slimt_oracle as so
@@ -361,7 +390,7 @@ def main():
             tok = np.zeros((16, SRC_LEN), dtype=np.uint32)
             for i, s in enumerate(chunk):
                 tok[i, :len(s)] = s
-            sl = so.shortlist_generate(np.concatenate(chunk), fr, offs, lists, synth.TINY.vocab)
+            sl = so.shortlist_generate(np.concatenate(chunk), fr, offs, lists, synth.TINY.vocab) if WL["shortlist"] else None
             orc = so.Oracle(synth.read_model(model_path))
             t0 = time.perf_counter()
             res = orc.forward(tok, np.array([len(s) for s in chunk]), LIMIT, shortlist=sl)
