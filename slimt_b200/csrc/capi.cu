@@ -189,7 +189,32 @@ int slimt_b200_translate(slimt_b200_model* model, slimt_b200_translate_io* io) {
   sb::Batcher batcher(io->max_words);
   for (size_t i = 0; i < io->n_sentences; i++) batcher.enqueue(i, io->offsets[i + 1] - io->offsets[i]);
 
-  std::vector<std::vector<uint32_t>> targets(io->n_sentences);
+  // record() (Model.cc:127-137) keeps each sentence's tokens up to and including its first EOS.  Each batch's kept
+  // tokens are packed into one block per batch (no per-sentence containers); the ragged output is written once every
+  // length is known.  The padded batch and the step-token matrix travel through one pinned staging block.
+  struct Done {
+    std::vector<size_t> ids;
+    std::vector<uint32_t> kept;  // the batch's sentences back to back, in batch row order
+  };
+  std::vector<Done> done;
+  std::vector<uint32_t> out_len(io->n_sentences, 0);
+  // staging layout: [padded tokens + lengths of the current batch][its step tokens]
+  size_t in_bytes = 0, steps_bytes = 0;
+  {
+    sb::Batcher plan(io->max_words);
+    for (size_t i = 0; i < io->n_sentences; i++) plan.enqueue(i, io->offsets[i + 1] - io->offsets[i]);
+    for (;;) {
+      size_t width = 0;
+      std::vector<size_t> b = plan.generate(&width);
+      if (b.empty()) break;
+      const size_t max_steps = static_cast<size_t>(io->limit_factor * static_cast<float>(width));
+      in_bytes = std::max(in_bytes, 4 * (b.size() * width + b.size()));
+      steps_bytes = std::max(steps_bytes, 4 * std::max<size_t>(1, max_steps) * b.size());
+    }
+  }
+  in_bytes = (in_bytes + 255) & ~size_t(255);
+  char* stage = c.staging_reserve(in_bytes + steps_bytes + 256);
+  if (!stage) return 1;
   io->target_tokens = 0, io->batches = 0, io->device_ms = 0;
   cudaSetDevice(c.device);
   cudaEvent_t e0, e1;
@@ -201,11 +226,15 @@ int slimt_b200_translate(slimt_b200_model* model, slimt_b200_translate_io* io) {
     if (batch.empty()) break;
     // convert(): Batch -> padded Input (Frontend.cc:30-40; Input.cc:20-47), pad id 0
     const size_t B = batch.size();
-    std::vector<uint32_t> tokens(B * width, 0u), lengths(B), words;
+    uint32_t* tokens = reinterpret_cast<uint32_t*>(stage);
+    uint32_t* lengths = tokens + B * width;
+    std::vector<uint32_t> words;
+    words.reserve(B * width);
     for (size_t r = 0; r < B; r++) {
       const size_t s = batch[r];
       const size_t len = io->offsets[s + 1] - io->offsets[s];
-      memcpy(tokens.data() + r * width, io->tokens + io->offsets[s], 4 * len);
+      memcpy(tokens + r * width, io->tokens + io->offsets[s], 4 * len);
+      memset(tokens + r * width + len, 0, 4 * (width - len));
       lengths[r] = static_cast<uint32_t>(len);
       words.insert(words.end(), io->tokens + io->offsets[s], io->tokens + io->offsets[s + 1]);
     }
@@ -213,26 +242,33 @@ int slimt_b200_translate(slimt_b200_model* model, slimt_b200_translate_io* io) {
     // while the GPU runs the encoder (the callback fires once the encoder kernels are queued)
     LazyShortlist lazy{&gen, &words, static_cast<size_t>(m.V), {}};
     const size_t max_steps = static_cast<size_t>(io->limit_factor * static_cast<float>(width));
-    std::vector<uint32_t> steps(std::max<size_t>(1, max_steps) * B);
+    uint32_t* steps = reinterpret_cast<uint32_t*>(stage + in_bytes);
     sb::ForwardArgs a;
-    a.tokens = tokens.data(), a.lengths = lengths.data(), a.B = B, a.T = width;
+    a.tokens = tokens, a.lengths = lengths, a.B = B, a.T = width;
     a.limit_factor = io->limit_factor;
     if (use_sl) a.shortlist_cb = lazy_shortlist_cb, a.shortlist_user = &lazy;
-    a.step_tokens = steps.data();
+    a.step_tokens = steps;
     if (sb::model_forward(m, a)) {
       cudaEventDestroy(e0), cudaEventDestroy(e1);
       return 1;
     }
-    // record() (Model.cc:127-137): keep tokens up to and including the first EOS
+    size_t kept_total = 0;
     for (size_t r = 0; r < B; r++) {
-      std::vector<uint32_t>& t = targets[batch[r]];
-      t.reserve(a.steps);
-      for (size_t st = 0; st < a.steps; st++) {
-        const uint32_t w = steps[st * B + r];
-        t.push_back(w);
-        if (w == 0u) break;
+      uint32_t n = 0;
+      while (n < a.steps) {
+        if (steps[n++ * B + r] == 0u) break;
       }
+      out_len[batch[r]] = n;
+      kept_total += n;
     }
+    std::vector<uint32_t> kept(kept_total);
+    size_t pos = 0;
+    for (size_t r = 0; r < B; r++) {
+      const uint32_t n = out_len[batch[r]];
+      for (uint32_t k = 0; k < n; k++) kept[pos + k] = steps[k * B + r];
+      pos += n;
+    }
+    done.push_back(Done{std::move(batch), std::move(kept)});
     io->target_tokens += a.target_tokens;
     io->batches += 1;
   }
@@ -243,17 +279,22 @@ int slimt_b200_translate(slimt_b200_model* model, slimt_b200_translate_io* io) {
   cudaEventDestroy(e0), cudaEventDestroy(e1);
   io->device_ms = ms;
 
-  uint64_t off = 0;
-  for (size_t i = 0; i < io->n_sentences; i++) {
-    if (io->out_offsets) io->out_offsets[i] = off;
-    if (io->out_tokens) {
-      if (off + targets[i].size() > io->out_capacity) {
-        sb::set_error("out_tokens capacity too small");
-        return 1;
+  std::vector<uint64_t> out_off(io->n_sentences + 1, 0);
+  for (size_t i = 0; i < io->n_sentences; i++) out_off[i + 1] = out_off[i] + out_len[i];
+  const uint64_t off = out_off[io->n_sentences];
+  if (io->out_tokens && off > io->out_capacity) {
+    sb::set_error("out_tokens capacity too small");
+    return 1;
+  }
+  if (io->out_offsets) memcpy(io->out_offsets, out_off.data(), 8 * io->n_sentences);
+  if (io->out_tokens) {
+    for (const Done& d : done) {
+      size_t pos = 0;
+      for (size_t s : d.ids) {
+        memcpy(io->out_tokens + out_off[s], d.kept.data() + pos, 4ul * out_len[s]);
+        pos += out_len[s];
       }
-      memcpy(io->out_tokens + off, targets[i].data(), 4 * targets[i].size());
     }
-    off += targets[i].size();
   }
   if (io->out_offsets) io->out_offsets[io->n_sentences] = off;
   io->kernel_launches = c.launches - l0;

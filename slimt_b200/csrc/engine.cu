@@ -86,11 +86,26 @@ void Context::destroy() {
   if (arena) cudaFree(arena);
   if (flush_buf) cudaFree(flush_buf);
   if (done_slots) cudaFreeHost(done_slots);
+  if (staging) cudaFreeHost(staging);
   for (auto& e : done_events)
     if (e) cudaEventDestroy(e);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   if (stream) cudaStreamDestroy(stream);
+}
+
+char* Context::staging_reserve(size_t bytes) {
+  if (bytes > staging_bytes) {
+    if (staging) cudaFreeHost(staging);
+    staging = nullptr, staging_bytes = 0;
+    const size_t want = bytes + bytes / 4;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&staging), want, cudaHostAllocDefault) != cudaSuccess) {
+      set_error("pinned staging allocation failed");
+      return nullptr;
+    }
+    staging_bytes = want;
+  }
+  return staging;
 }
 
 cudaEvent_t Context::pooled_event() {

@@ -44,6 +44,10 @@ struct Context {
   size_t arena_used = 0;
   char* flush_buf = nullptr;
   size_t flush_bytes = 0;
+  // pinned host staging of the service path (padded batch in, step tokens out): grown on demand, reused across calls
+  char* staging = nullptr;
+  size_t staging_bytes = 0;
+  char* staging_reserve(size_t bytes);
   uint64_t launches = 0;
   uint64_t h2d_bytes = 0, d2h_bytes = 0;
   // early-exit polling of the decode loop: pinned slots + events, so the host never drains the stream
