@@ -260,13 +260,16 @@ __global__ void __launch_bounds__(kThreadsEa, 1) enc_attention_kernel(const __gr
         float acc[kDH];
 #pragma unroll
         for (int d = 0; d < kDH; d++) acc[d] = 0.0f;
+        // every probability of the row divides by `sum`: reciprocal once, three FFMAs per key (exact_math.cuh)
+        const float sum_rcp = rcp_refined(sum);
+        const float sum_lo = div_guard_lo(sum);
 #pragma unroll
         for (int j0 = 0; j0 < TMAX; j0 += 4) {
           if (j0 < wmax) {
 #pragma unroll
             for (int u = 0; u < 4; u++) {
               if (j0 + u < wmax) {
-                const float p = j0 + u < len ? __fdiv_rn(S[j0 + u], sum) : 0.0f;
+                const float p = j0 + u < len ? div_by_rcp(S[j0 + u], sum, sum_rcp, sum_lo) : 0.0f;
                 const float* vp = Vs + (krow0 + j0 + u) * kStride;
 #pragma unroll
                 for (int d = 0; d < kDH; d += 4) {

@@ -44,6 +44,35 @@ __global__ void quant_kernel(float aq, unsigned long long* bad, uint32_t* first_
   }
 }
 
+// 3. div_by_rcp(n, d, rcp_refined(d), div_guard_lo(d)) == __fdiv_rn(n, d): every float n for a set of divisors, and
+// pseudo-random (n, d) pairs over all bit patterns
+__global__ void div_kernel(float d, unsigned long long* bad, uint32_t* first_bad) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const float r = rcp_refined(d), lo = div_guard_lo(d);
+  for (uint64_t k = blockIdx.x * blockDim.x + threadIdx.x; k < (1ull << 32); k += stride) {
+    const float n = __uint_as_float(static_cast<uint32_t>(k));
+    const float a = div_by_rcp(n, d, r, lo), b = __fdiv_rn(n, d);
+    if (__float_as_uint(a) != __float_as_uint(b) && !(a != a && b != b)) {
+      if (atomicAdd(bad, 1ull) == 0) *first_bad = static_cast<uint32_t>(k);
+    }
+  }
+}
+__global__ void div_random_kernel(uint64_t pairs, unsigned long long* bad, uint32_t* first_bad) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t k = blockIdx.x * blockDim.x + threadIdx.x; k < pairs; k += stride) {
+    uint64_t z = k * 0x9E3779B97F4A7C15ull + 0x1234567ull;  // splitmix64
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const float n = __uint_as_float(static_cast<uint32_t>(z));
+    const float d = __uint_as_float(static_cast<uint32_t>(z >> 32));
+    const float a = div_by_rcp(n, d, rcp_refined(d), div_guard_lo(d)), b = __fdiv_rn(n, d);
+    if (__float_as_uint(a) != __float_as_uint(b) && !(a != a && b != b)) {
+      if (atomicAdd(bad, 1ull) == 0) *first_bad = static_cast<uint32_t>(z);
+    }
+  }
+}
+
 int main() {
   // ---- 1. expf on every non-positive float
   const uint32_t chunk = 1u << 24;
@@ -96,5 +125,34 @@ int main() {
     printf("{\"check\": \"quantize1 vs cvtps2dq formulation, all 2^32 floats\", \"aq\": %g, \"mismatches\": %llu, \"first_bad_bits\": \"0x%08x\", \"err\": \"%s\"}\n",
            aq, b, f, cudaGetErrorString(cudaGetLastError()));
   }
-  return bad.load() != 0;
+  // ---- 3. shared-divisor division
+  unsigned long long div_bad = 0;
+  const float divisors[] = {1.0f, 1.0000001f, 1.5f, 1.9999999f, 2.0f, 3.0f, 7.3891f, 31.999998f, 0.001f, 0.0010000469f,
+                            0.73f, 1.2345678f, 12.5f, 123.456f, 9999.5f, 1e-30f, 1e30f, 0.0f, 5e-39f};
+  for (float dv : divisors) {
+    cudaMemset(dbad, 0, 8);
+    cudaMemset(dfirst, 0, 4);
+    div_kernel<<<148 * 8, 256>>>(dv, dbad, dfirst);
+    unsigned long long b;
+    uint32_t f;
+    cudaMemcpy(&b, dbad, 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(&f, dfirst, 4, cudaMemcpyDeviceToHost);
+    div_bad += b;
+    printf("{\"check\": \"div_by_rcp vs __fdiv_rn, all 2^32 numerators\", \"divisor\": %.9g, \"mismatches\": %llu, \"first_bad_bits\": \"0x%08x\", \"err\": \"%s\"}\n",
+           dv, b, f, cudaGetErrorString(cudaGetLastError()));
+  }
+  {
+    cudaMemset(dbad, 0, 8);
+    cudaMemset(dfirst, 0, 4);
+    const uint64_t pairs = 1ull << 36;
+    div_random_kernel<<<148 * 8, 256>>>(pairs, dbad, dfirst);
+    unsigned long long b;
+    uint32_t f;
+    cudaMemcpy(&b, dbad, 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(&f, dfirst, 4, cudaMemcpyDeviceToHost);
+    div_bad += b;
+    printf("{\"check\": \"div_by_rcp vs __fdiv_rn, pseudo-random (n, d) bit patterns\", \"pairs\": %llu, \"mismatches\": %llu, \"first_bad_bits\": \"0x%08x\", \"err\": \"%s\"}\n",
+           static_cast<unsigned long long>(pairs), b, f, cudaGetErrorString(cudaGetLastError()));
+  }
+  return bad.load() != 0 || div_bad != 0;
 }
