@@ -312,6 +312,9 @@ def main():
     else:
         all_tokens, all_e2e_tokens, all_launches = float(tokens_per_step * args.steps), float(e2e_tokens), launches
 
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
 
