@@ -71,6 +71,8 @@ __global__ void self_attention_kernel(const float* __restrict__ Q, const float* 
   const int E = H * DH;
   const int len = min(static_cast<int>(lengths[b]), T);
   const int Tp = T | 1;
+  __shared__ uint64_t exp_tab[32];
+  if (threadIdx.x < 32) exp_tab[threadIdx.x] = kExp2fTab[threadIdx.x];
   float* Ks = smem_f;
   float* Vs = Ks + static_cast<size_t>(T) * DH;
   float* Ss = Vs + static_cast<size_t>(T) * DH;
@@ -95,8 +97,26 @@ __global__ void self_attention_kernel(const float* __restrict__ Q, const float* 
         const float4 t = *reinterpret_cast<const float4*>(Q + off + d);
         qv[d] = t.x, qv[d + 1] = t.y, qv[d + 2] = t.z, qv[d + 3] = t.w;
       }
+      // Four keys at a time: each dot product stays the reference's sequential fma chain, but four independent
+      // chains (and four expf evaluations) are in flight per thread -- with one block per SM at long T there are
+      // few warps to hide a single chain's latency behind.
       float mx = -3.402823466e+38f;
-      for (int j = 0; j < len; j++) {
+      int j = 0;
+      for (; j + 4 <= len; j += 4) {
+        const float* kp = Ks + j * DH;
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+        for (int d = 0; d < DH; d++) {
+          s0 = fmaf(qv[d], kp[d], s0);
+          s1 = fmaf(qv[d], kp[DH + d], s1);
+          s2 = fmaf(qv[d], kp[2 * DH + d], s2);
+          s3 = fmaf(qv[d], kp[3 * DH + d], s3);
+        }
+        s0 = __fmul_rn(dk, s0), s1 = __fmul_rn(dk, s1), s2 = __fmul_rn(dk, s2), s3 = __fmul_rn(dk, s3);
+        S[j] = s0, S[j + 1] = s1, S[j + 2] = s2, S[j + 3] = s3;
+        mx = fmaxf(fmaxf(fmaxf(mx, s0), fmaxf(s1, s2)), s3);
+      }
+      for (; j < len; j++) {
         float s = 0.0f;
 #pragma unroll
         for (int d = 0; d < DH; d++) s = fmaf(qv[d], Ks[j * DH + d], s);
@@ -105,15 +125,27 @@ __global__ void self_attention_kernel(const float* __restrict__ Q, const float* 
         mx = fmaxf(mx, s);
       }
       float sum = 0.0f;
-      for (int j = 0; j < len; j++) {
-        const float e = expf_glibc(__fsub_rn(S[j], mx));
+      j = 0;
+      for (; j + 4 <= len; j += 4) {
+        const float e0 = expf_glibc_nonpos_tab(__fsub_rn(S[j], mx), exp_tab);
+        const float e1 = expf_glibc_nonpos_tab(__fsub_rn(S[j + 1], mx), exp_tab);
+        const float e2 = expf_glibc_nonpos_tab(__fsub_rn(S[j + 2], mx), exp_tab);
+        const float e3 = expf_glibc_nonpos_tab(__fsub_rn(S[j + 3], mx), exp_tab);
+        S[j] = e0, S[j + 1] = e1, S[j + 2] = e2, S[j + 3] = e3;
+        sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, e0), e1), e2), e3);
+      }
+      for (; j < len; j++) {
+        const float e = expf_glibc_nonpos_tab(__fsub_rn(S[j], mx), exp_tab);
         S[j] = e;
         sum = __fadd_rn(sum, e);
       }
 #pragma unroll
       for (int d = 0; d < DH; d++) acc[d] = 0.0f;
-      for (int j = 0; j < len; j++) {
-        const float p = __fdiv_rn(S[j], sum);
+      // every probability of the row divides by `sum`: reciprocal once, three FFMAs per key (exact_math.cuh)
+      const float sum_rcp = rcp_refined(sum);
+      const float sum_lo = div_guard_lo(sum);
+      for (j = 0; j < len; j++) {
+        const float p = div_by_rcp(S[j], sum, sum_rcp, sum_lo);
 #pragma unroll
         for (int d = 0; d < DH; d++) acc[d] = fmaf(p, Vs[j * DH + d], acc[d]);
       }
