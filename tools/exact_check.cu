@@ -73,6 +73,21 @@ __global__ void div_random_kernel(uint64_t pairs, unsigned long long* bad, uint3
   }
 }
 
+// 4. sigmoid with the branch-free quotient == sigmoid with __fdiv_rn, every float
+__global__ void sigmoid_kernel(unsigned long long* bad, uint32_t* first_bad) {
+  __shared__ uint64_t tab[32];
+  if (threadIdx.x < 32) tab[threadIdx.x] = kExp2fTab[threadIdx.x];
+  __syncthreads();
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint64_t k = blockIdx.x * blockDim.x + threadIdx.x; k < (1ull << 32); k += stride) {
+    const float x = __uint_as_float(static_cast<uint32_t>(k));
+    const float a = sigmoid_ref_tab(x, tab), b = sigmoid_ref_tab_plain(x, tab);
+    if (__float_as_uint(a) != __float_as_uint(b) && !(a != a && b != b)) {
+      if (atomicAdd(bad, 1ull) == 0) *first_bad = static_cast<uint32_t>(k);
+    }
+  }
+}
+
 int main() {
   // ---- 1. expf on every non-positive float
   const uint32_t chunk = 1u << 24;
@@ -153,6 +168,18 @@ int main() {
     div_bad += b;
     printf("{\"check\": \"div_by_rcp vs __fdiv_rn, pseudo-random (n, d) bit patterns\", \"pairs\": %llu, \"mismatches\": %llu, \"first_bad_bits\": \"0x%08x\", \"err\": \"%s\"}\n",
            static_cast<unsigned long long>(pairs), b, f, cudaGetErrorString(cudaGetLastError()));
+  }
+  {
+    cudaMemset(dbad, 0, 8);
+    cudaMemset(dfirst, 0, 4);
+    sigmoid_kernel<<<148 * 8, 256>>>(dbad, dfirst);
+    unsigned long long b;
+    uint32_t f;
+    cudaMemcpy(&b, dbad, 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(&f, dfirst, 4, cudaMemcpyDeviceToHost);
+    div_bad += b;
+    printf("{\"check\": \"sigmoid, branch-free quotient vs __fdiv_rn, all 2^32 floats\", \"mismatches\": %llu, \"first_bad_bits\": \"0x%08x\", \"err\": \"%s\"}\n",
+           b, f, cudaGetErrorString(cudaGetLastError()));
   }
   return bad.load() != 0 || div_bad != 0;
 }
