@@ -73,19 +73,23 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe).  nvidia-smi needs a
+    moment to start, so the sampler is started before the warm-up; mark() brackets the timed region and only samples
+    read inside it count (if the region is too short to contain one, the samples nearest to it -- all taken under the
+    same load, warm-up or end-to-end passes -- are used and that is said in `window`)."""
 
     def __init__(self, index: int):
-        self.rows = []
+        self.rows = []  # (host time when read, fields)
         self.proc = None
         self.index = index
+        self.t0 = self.t1 = None
 
     def start(self):
         q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -93,15 +97,26 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= self.t1 + 0.03]
+        window = "timed region"
+        if not inside:
+            inside = [r for _, r in self.rows]
+            window = "warm-up + timed region + end-to-end passes (timed region shorter than one sample)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1])), mx.append(float(r[2]))
             except (ValueError, IndexError):
@@ -110,7 +125,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def build_assets(tmp: str, rank: int):
@@ -251,11 +266,12 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         resident_pass()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     launches0 = ctx.launches()
     step_ms, tokens_per_step = [], 0
     if args.profiler_range:
@@ -271,7 +287,7 @@ def main():
         ctx.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
     barrier()
-    clocks = sampler.stop()
+    sampler.mark_end()
     total_ms = sum(step_ms)
 
     # ---- end-to-end arm through the public C-ABI call with host buffers (ragged tokens/offsets in, ragged targets
@@ -294,6 +310,8 @@ def main():
         e2e_tokens += st["target_tokens"]
         e2e_stats = st
     barrier()
+
+    clocks = sampler.stop()
 
     # ---- per-kernel event timing: one extra profiled pass (not part of the timed region)
     ctx.profile(True)
