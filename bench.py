@@ -51,6 +51,10 @@ WORKLOADS = {
     "base_shortlist": dict(dims="BASE", shortlist=True, sentences=4096, length=32, max_words=4096 * 32,
                            desc="base int8 (emb 512, ffn 2048, 6 enc / 2 SSRU dec, vocab 32000, random-init) with lexical "
                                 "shortlist, 4096 synthetic sentences x 32 tokens per GPU (BASELINE.json configs[2])"),
+    "tiny_len64": dict(dims="TINY", shortlist=True, sentences=2048, length=64, max_words=2048 * 64,
+                       desc="tiny11 int8 with lexical shortlist, 2048 synthetic sentences x 64 tokens per GPU (the same 131072 "
+                            "source tokens as the headline at twice the sentence length: the two-key-block recompute "
+                            "cross-attention and the T = 64 fused encoder attention)"),
     "mixed": dict(dims="TINY", shortlist=True, sentences=16384, length=(8, 256), max_words=1 << 20,
                   desc="tiny11 int8 with lexical shortlist, mixed-length sweep: 16384 synthetic sentences per GPU per step, "
                        "lengths U{8..256}, length-bucketed by the Batcher into batches of <= 1048576 padded words "

@@ -16,7 +16,11 @@
 //   V phase   D_v[feature][key row]   = Wv (A, M = 128 per block) x qa_v tile (B, N = 128): TMEM lane = feature, so
 //             a thread accumulates its output feature over the keys in order, probabilities broadcast from smem.
 // The MMA of the next phase overlaps the drain of the current one (D_k and D_v are separate TMEM regions).
-// Supported: E = 256, 8 heads of 32, S <= 32.  Everything else uses the cached kernel (cross_attention.cu).
+// Sentences longer than 32 tokens (template parameter KB = 2: up to 64) take two 32-key blocks of the group's 128 lanes,
+// so a group holds 4 / KB sentences: the softmax maximum and the key-ordered sum then span the KB warps that hold a
+// sentence's blocks (partial maxima and the exponentials meet in shared memory under a barrier of just those warps),
+// and a V-phase thread runs ONE chain over the sentence's 32 * KB keys instead of two sentences' chains.
+// Supported: E = 256, 8 heads of 32, S <= 64.  Everything else uses the cached kernel (cross_attention.cu).
 #include <stdio.h>
 
 #include "exact_math.cuh"
@@ -42,7 +46,8 @@ struct Smem {
   static constexpr int qs = av + 32 * 1024;           // f32 [4][256]
   static constexpr int ps = qs + kGroup * kE * 4;     // f32 [4][8][32]
   static constexpr int pbk = ps + kGroup * kH * kKeys * 4;  // f32 [256]
-  static constexpr int exp_tab = pbk + kE * 4;        // u64 [32]
+  static constexpr int pmax = pbk + kE * 4;           // f32 [4 key blocks][8 heads]: per-block score maxima (KB > 1)
+  static constexpr int exp_tab = pmax + kGroup * kH * 4;  // u64 [32]
   static constexpr int bars = exp_tab + 32 * 8;
   // w_full ak_full av_full ak_free av_free k_done v_done k_drained v_drained
   static constexpr int n_bars = 9;
@@ -50,7 +55,9 @@ struct Smem {
   static constexpr int total = tmem_slot + 16 + 1024;
 };
 
+template <int KB>  // 32-key blocks per sentence (1: S <= 32, 2: S <= 64)
 __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const __grid_constant__ CrossRcArgs a) {
+  constexpr int NS = kGroup / KB;  // sentences per group
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* s_wk = smem + Smem::wk;
@@ -60,6 +67,7 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
   float* s_q = reinterpret_cast<float*>(smem + Smem::qs);
   float* s_p = reinterpret_cast<float*>(smem + Smem::ps);
   float* s_pbk = reinterpret_cast<float*>(smem + Smem::pbk);
+  float* s_pmax = reinterpret_cast<float*>(smem + Smem::pmax);
   uint64_t* exp_tab = reinterpret_cast<uint64_t*>(smem + Smem::exp_tab);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
   uint64_t* w_full = bars;
@@ -110,7 +118,7 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
   const uint32_t tmem_k = tmem;         // 256 columns: features
   const uint32_t tmem_v = tmem + 256;   // 2 blocks x 128 columns: key rows of the group
 
-  const int n_groups = (a.B + kGroup - 1) / kGroup;
+  const int n_groups = (a.B + NS - 1) / NS;
 
   if (warp == 0) {
     // ===== TMA producer
@@ -126,20 +134,24 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
       uint32_t it = 0;
       for (int g = blockIdx.x; g < n_groups; g += gridDim.x, it++) {
         const uint32_t ph = it & 1;
-        const int b0 = g * kGroup;
+        const int b0 = g * NS;
+        // slot = 32 key rows: sentence slot / KB, its key block slot % KB (rows past the sentence's length -- the next
+        // sentence's, or zero fill past the tensor -- are masked by the consumers)
         mbar_wait(ak_free, ph ^ 1);
         mbar_expect_tx(ak_full, 32 * 1024);
         for (int kb = 0; kb < 2; kb++)
-          for (int j = 0; j < kGroup; j++) {
+          for (int slot = 0; slot < kGroup; slot++) {
+            const int j = slot / KB;
             const int b = b0 + j < a.B ? b0 + j : b0;  // tail group: repeat a valid sentence, its lanes are ignored
-            tma_load_2d(s_ak + kb * 16384 + j * 4096, &a.map_ak, ak_full, kb * 128, b * a.T);
+            tma_load_2d(s_ak + kb * 16384 + slot * 4096, &a.map_ak, ak_full, kb * 128, b * a.T + (slot % KB) * kKeys);
           }
         mbar_wait(av_free, ph ^ 1);
         mbar_expect_tx(av_full, 32 * 1024);
         for (int kb = 0; kb < 2; kb++)
-          for (int j = 0; j < kGroup; j++) {
+          for (int slot = 0; slot < kGroup; slot++) {
+            const int j = slot / KB;
             const int b = b0 + j < a.B ? b0 + j : b0;
-            tma_load_2d(s_av + kb * 16384 + j * 4096, &a.map_av, av_full, kb * 128, b * a.T);
+            tma_load_2d(s_av + kb * 16384 + slot * 4096, &a.map_av, av_full, kb * 128, b * a.T + (slot % KB) * kKeys);
           }
       }
     }
@@ -191,43 +203,47 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
     const float pbv = a.pb_v[v_feat];
     // Global inputs of a group (its query rows and sentence lengths) are fetched one group ahead into registers, so
     // their latency hides behind the previous group's arithmetic instead of opening every iteration.
-    static_assert(kGroup * kE == 2 * kConsThreads, "two query floats per consumer thread");
-    const int vj0 = (sub >> 1) * 2;
-    float q_nx[2];
-    int len_nx[3];  // K phase: sentence qd; V phase: sentences vj0, vj0 + 1
+    constexpr int kQPer = NS * kE / kConsThreads;  // query floats per consumer thread: 2 (KB = 1) or 1 (KB = 2)
+    static_assert(NS * kE == kQPer * kConsThreads, "query floats per consumer thread");
+    const int kj = qd / KB;             // K phase: this warp's sentence of the group ...
+    const int kblk = qd % KB;           // ... and which of its key blocks sits in the warp's lane quadrant
+    const int key = kblk * kKeys + lane;
+    const int vj0 = KB == 1 ? (sub >> 1) * 2 : (sub >> 1);  // V phase: first (KB = 1: of two) sentence of this warp
+    float q_nx[kQPer];
+    int len_nx[3];  // K phase: sentence kj; V phase: sentences vj0 (and vj0 + 1 when KB = 1)
     auto fetch_group = [&](int g) {
-      const int b0 = g * kGroup;
+      const int b0 = g * NS;
 #pragma unroll
-      for (int r = 0; r < 2; r++) {
+      for (int r = 0; r < kQPer; r++) {
         const int i = ct + r * kConsThreads;
         const int b = b0 + i / kE;
         q_nx[r] = (g < n_groups && b < a.B) ? __ldg(a.q + static_cast<size_t>(b) * kE + (i % kE)) : 0.0f;
       }
-      const int js[3] = {qd, vj0, vj0 + 1};
+      const int js[3] = {kj, vj0, vj0 + 1};
 #pragma unroll
       for (int r = 0; r < 3; r++) {
         const int b = b0 + js[r];
-        len_nx[r] = (g < n_groups && b < a.B) ? min(static_cast<int>(__ldg(a.lengths + b)), a.T) : 0;
+        len_nx[r] = (g < n_groups && js[r] < NS && b < a.B) ? min(static_cast<int>(__ldg(a.lengths + b)), a.T) : 0;
       }
     };
     fetch_group(blockIdx.x);
     uint32_t it = 0;
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x, it++) {
       const uint32_t ph = it & 1;
-      const int b0 = g * kGroup;
+      const int b0 = g * NS;
       // the group's query rows (s_q is free: the previous group's K phase ended before its mid-group barrier)
-      s_q[ct] = q_nx[0];
-      s_q[ct + kConsThreads] = q_nx[1];
+#pragma unroll
+      for (int r = 0; r < kQPer; r++) s_q[ct + r * kConsThreads] = q_nx[r];
       const int len_k = len_nx[0];
       const int len_v[2] = {len_nx[1], len_nx[2]};
       fetch_group(g + gridDim.x);
       named_bar_sync(1, kConsThreads);
 
-      // ---- K phase: quadrant = sentence, lane = key, two heads per warp
+      // ---- K phase: quadrant = 32 keys of a sentence, lane = key, two heads per warp
       {
-        const int j = qd;
+        const int j = kj;
         const int b = b0 + j;
-        const bool valid = lane < len_k;
+        const bool valid = key < len_k;
         mbar_wait(k_done, ph);
         tc_fence_after();
         uint32_t v0[32], v1[32];
@@ -265,6 +281,8 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
         // softmax over the sentence's keys (slimt/TensorOps.cc:282-315): max, exp, sum in key order, divide.  Both
         // heads advance together: nothing is stored between the two expf evaluations (a store would pin the second
         // one's table load behind it), so their double-precision chains interleave.
+        constexpr int kRow = KB * kKeys;  // probabilities of one (sentence, head)
+        float* prow = s_p + (j * kH + h0) * kRow;
         float mx[2], e[2], sum[2];
 #pragma unroll
         for (int hh = 0; hh < 2; hh++) mx[hh] = valid ? sc[hh] : -3.402823466e+38f;
@@ -273,45 +291,57 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
 #pragma unroll
           for (int hh = 0; hh < 2; hh++) mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], o));
         }
+        if constexpr (KB > 1) {
+          // the sentence's other key block lives in the neighbouring quadrant's warp with the same head pair: the two
+          // block maxima meet in shared memory (the maximum of a set does not depend on the order it is formed in)
+          if (lane < 2) s_pmax[qd * kH + h0 + lane] = mx[lane];
+          named_bar_sync(2 + kj * 4 + sub, KB * 32);
+#pragma unroll
+          for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+            for (int o = 0; o < KB; o++) mx[hh] = fmaxf(mx[hh], s_pmax[(kj * KB + o) * kH + h0 + hh]);
+        }
 #pragma unroll
         for (int hh = 0; hh < 2; hh++) e[hh] = expf_glibc_nonpos_tab(__fsub_rn(sc[hh], mx[hh]), exp_tab);
 #pragma unroll
         for (int hh = 0; hh < 2; hh++) {
           e[hh] = valid ? e[hh] : 0.0f;
-          s_p[(j * kH + h0 + hh) * kKeys + lane] = e[hh];
+          prow[hh * kRow + key] = e[hh];
           sum[hh] = 0.0f;
         }
-        __syncwarp();
+        if constexpr (KB > 1) named_bar_sync(2 + kj * 4 + sub, KB * 32);
+        else __syncwarp();
 #pragma unroll
-        for (int l = 0; l < kKeys; l += 4) {
+        for (int l = 0; l < kRow; l += 4) {
 #pragma unroll
           for (int hh = 0; hh < 2; hh++) {
-            const float4 t = *reinterpret_cast<const float4*>(s_p + (j * kH + h0 + hh) * kKeys + l);
+            const float4 t = *reinterpret_cast<const float4*>(prow + hh * kRow + l);
             sum[hh] = __fadd_rn(sum[hh], t.x);
             sum[hh] = __fadd_rn(sum[hh], t.y);
             sum[hh] = __fadd_rn(sum[hh], t.z);
             sum[hh] = __fadd_rn(sum[hh], t.w);
           }
         }
-        __syncwarp();
+        if constexpr (KB > 1) named_bar_sync(2 + kj * 4 + sub, KB * 32);  // every warp of the sentence has read the e's
+        else __syncwarp();
 #pragma unroll
         for (int hh = 0; hh < 2; hh++) {
           const float p = valid ? __fdiv_rn(e[hh], sum[hh]) : 0.0f;
-          s_p[(j * kH + h0 + hh) * kKeys + lane] = p;
-          if (a.attn_head0 != nullptr && h0 + hh == 0 && b < a.B && lane < a.T)
-            a.attn_head0[static_cast<size_t>(b) * a.T + lane] = p;
+          prow[hh * kRow + key] = p;
+          if (a.attn_head0 != nullptr && h0 + hh == 0 && b < a.B && key < a.T)
+            a.attn_head0[static_cast<size_t>(b) * a.T + key] = p;
         }
       }
       named_bar_sync(1, kConsThreads);
 
-      // ---- V phase: lane = output feature, two sentences per warp
+      // ---- V phase: lane = output feature; KB = 1: two sentences per warp, KB = 2: one sentence of up to 64 keys
       {
         mbar_wait(v_done, ph);
         tc_fence_after();
         uint32_t v0[32], v1[32];
-        const int j0 = vj0;
-        tmem_ld32_nowait(tmem_v + lane_sel + v_mb * 128 + j0 * 32, v0);
-        tmem_ld32_nowait(tmem_v + lane_sel + v_mb * 128 + j0 * 32 + 32, v1);
+        const int c0 = (sub >> 1) * 64;  // the warp's 64 key columns of the group
+        tmem_ld32_nowait(tmem_v + lane_sel + v_mb * 128 + c0, v0);
+        tmem_ld32_nowait(tmem_v + lane_sel + v_mb * 128 + c0 + 32, v1);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -321,40 +351,81 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
           if (a.out_f32) a.out_f32[off] = acc;
           for (int k = 0; k < a.qo.n; k++) a.qo.ptr[k][off] = static_cast<int8_t>(quantize1(acc, a.qo.aq[k]));
         };
-        if (len_v[0] == kKeys && len_v[1] == kKeys && b0 + j0 + 1 < a.B) {
-          // both sentences full: their two chains advance together
-          const float* pr0 = s_p + (j0 * kH + v_head) * kKeys;
-          const float* pr1 = pr0 + kH * kKeys;
-          float acc0 = 0.0f, acc1 = 0.0f;
+        constexpr int kRow = KB * kKeys;
+        if constexpr (KB == 1) {
+          const int j0 = vj0;
+          if (len_v[0] == kKeys && len_v[1] == kKeys && b0 + j0 + 1 < a.B) {
+            // both sentences full: their two chains advance together
+            const float* pr0 = s_p + (j0 * kH + v_head) * kKeys;
+            const float* pr1 = pr0 + kH * kKeys;
+            float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll
-          for (int l = 0; l < kKeys; l += 4) {
-            const float4 p0 = *reinterpret_cast<const float4*>(pr0 + l);
-            const float4 p1 = *reinterpret_cast<const float4*>(pr1 + l);
-            acc0 = fmaf(p0.x, dequant1(static_cast<int>(v0[l]), a.um_v, pbv), acc0);
-            acc1 = fmaf(p1.x, dequant1(static_cast<int>(v1[l]), a.um_v, pbv), acc1);
-            acc0 = fmaf(p0.y, dequant1(static_cast<int>(v0[l + 1]), a.um_v, pbv), acc0);
-            acc1 = fmaf(p1.y, dequant1(static_cast<int>(v1[l + 1]), a.um_v, pbv), acc1);
-            acc0 = fmaf(p0.z, dequant1(static_cast<int>(v0[l + 2]), a.um_v, pbv), acc0);
-            acc1 = fmaf(p1.z, dequant1(static_cast<int>(v1[l + 2]), a.um_v, pbv), acc1);
-            acc0 = fmaf(p0.w, dequant1(static_cast<int>(v0[l + 3]), a.um_v, pbv), acc0);
-            acc1 = fmaf(p1.w, dequant1(static_cast<int>(v1[l + 3]), a.um_v, pbv), acc1);
+            for (int l = 0; l < kKeys; l += 4) {
+              const float4 p0 = *reinterpret_cast<const float4*>(pr0 + l);
+              const float4 p1 = *reinterpret_cast<const float4*>(pr1 + l);
+              acc0 = fmaf(p0.x, dequant1(static_cast<int>(v0[l]), a.um_v, pbv), acc0);
+              acc1 = fmaf(p1.x, dequant1(static_cast<int>(v1[l]), a.um_v, pbv), acc1);
+              acc0 = fmaf(p0.y, dequant1(static_cast<int>(v0[l + 1]), a.um_v, pbv), acc0);
+              acc1 = fmaf(p1.y, dequant1(static_cast<int>(v1[l + 1]), a.um_v, pbv), acc1);
+              acc0 = fmaf(p0.z, dequant1(static_cast<int>(v0[l + 2]), a.um_v, pbv), acc0);
+              acc1 = fmaf(p1.z, dequant1(static_cast<int>(v1[l + 2]), a.um_v, pbv), acc1);
+              acc0 = fmaf(p0.w, dequant1(static_cast<int>(v0[l + 3]), a.um_v, pbv), acc0);
+              acc1 = fmaf(p1.w, dequant1(static_cast<int>(v1[l + 3]), a.um_v, pbv), acc1);
+            }
+            emit(b0 + j0, acc0);
+            emit(b0 + j0 + 1, acc1);
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 2; jj++) {
+              const int j = j0 + jj;
+              const int b = b0 + j;
+              if (b >= a.B) continue;
+              // ragged sentence: only its own keys take part (the rows beyond belong to the next sentence)
+              const int len = len_v[jj];
+              const float* pr = s_p + (j * kH + v_head) * kKeys;
+              const uint32_t* vv = jj == 0 ? v0 : v1;
+              float acc = 0.0f;
+#pragma unroll
+              for (int l = 0; l < kKeys; l++) {
+                if (l < len) acc = fmaf(pr[l], dequant1(static_cast<int>(vv[l]), a.um_v, pbv), acc);
+              }
+              emit(b, acc);
+            }
           }
-          emit(b0 + j0, acc0);
-          emit(b0 + j0 + 1, acc1);
         } else {
-#pragma unroll
-          for (int jj = 0; jj < 2; jj++) {
-            const int j = j0 + jj;
-            const int b = b0 + j;
-            if (b >= a.B) continue;
-            // ragged sentence: only its own keys take part (the rows beyond belong to the next sentence)
-            const int len = len_v[jj];
-            const float* pr = s_p + (j * kH + v_head) * kKeys;
-            const uint32_t* vv = jj == 0 ? v0 : v1;
+          // one sentence, one chain over its keys in order: block 0 (v0) then block 1 (v1)
+          const int j = vj0;
+          const int b = b0 + j;
+          if (b < a.B) {
+            const int len = len_v[0];
+            const float* pr = s_p + (j * kH + v_head) * kRow;
             float acc = 0.0f;
+            if (len == kRow) {
 #pragma unroll
-            for (int l = 0; l < kKeys; l++) {
-              if (l < len) acc = fmaf(pr[l], dequant1(static_cast<int>(vv[l]), a.um_v, pbv), acc);
+              for (int l = 0; l < kKeys; l += 4) {
+                const float4 p = *reinterpret_cast<const float4*>(pr + l);
+                acc = fmaf(p.x, dequant1(static_cast<int>(v0[l]), a.um_v, pbv), acc);
+                acc = fmaf(p.y, dequant1(static_cast<int>(v0[l + 1]), a.um_v, pbv), acc);
+                acc = fmaf(p.z, dequant1(static_cast<int>(v0[l + 2]), a.um_v, pbv), acc);
+                acc = fmaf(p.w, dequant1(static_cast<int>(v0[l + 3]), a.um_v, pbv), acc);
+              }
+#pragma unroll
+              for (int l = 0; l < kKeys; l += 4) {
+                const float4 p = *reinterpret_cast<const float4*>(pr + kKeys + l);
+                acc = fmaf(p.x, dequant1(static_cast<int>(v1[l]), a.um_v, pbv), acc);
+                acc = fmaf(p.y, dequant1(static_cast<int>(v1[l + 1]), a.um_v, pbv), acc);
+                acc = fmaf(p.z, dequant1(static_cast<int>(v1[l + 2]), a.um_v, pbv), acc);
+                acc = fmaf(p.w, dequant1(static_cast<int>(v1[l + 3]), a.um_v, pbv), acc);
+              }
+            } else {
+#pragma unroll
+              for (int l = 0; l < kKeys; l++) {
+                if (l < len) acc = fmaf(pr[l], dequant1(static_cast<int>(v0[l]), a.um_v, pbv), acc);
+              }
+#pragma unroll
+              for (int l = 0; l < kKeys; l++) {
+                if (kKeys + l < len) acc = fmaf(pr[kKeys + l], dequant1(static_cast<int>(v1[l]), a.um_v, pbv), acc);
+              }
             }
             emit(b, acc);
           }
@@ -370,16 +441,18 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
 
 }  // namespace
 
-bool cross_attention_rc_supported(int E, int H, int dh, int S) { return E == kE && H == kH && dh == kDH && S >= 1 && S <= kKeys; }
+bool cross_attention_rc_supported(int E, int H, int dh, int S) {
+  return E == kE && H == kH && dh == kDH && S >= 1 && S <= 2 * kKeys;
+}
 
 int launch_cross_attention_rc(const CrossRcArgs& a, int num_sms, cudaStream_t stream) {
   if (a.B == 0) return 0;
-  const int groups = (a.B + kGroup - 1) / kGroup;
-  if (cudaFuncSetAttribute(cross_attention_rc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total) !=
-      cudaSuccess)
-    return 1;
-  return launch_pdl(cross_attention_rc_kernel, dim3(groups < num_sms ? groups : num_sms), dim3(kThreadsRc), Smem::total, stream,
-                    a) != cudaSuccess;
+  const bool two = a.T > kKeys;  // sentences of 33..64 tokens take two key blocks each
+  const int per_group = two ? kGroup / 2 : kGroup;
+  const int groups = (a.B + per_group - 1) / per_group;
+  auto kern = two ? cross_attention_rc_kernel<2> : cross_attention_rc_kernel<1>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total) != cudaSuccess) return 1;
+  return launch_pdl(kern, dim3(groups < num_sms ? groups : num_sms), dim3(kThreadsRc), Smem::total, stream, a) != cudaSuccess;
 }
 
 }  // namespace sb

@@ -953,7 +953,8 @@ int model_forward(Model& m, ForwardArgs& a) {
         qadd(k.qo, caq, L.ctx.o.aq);
         k.attn_head0 = last ? d_align : nullptr;
         const double Bd = B, Ed = E;
-        LaunchScope ls(c, "dec_cross_attention_rc", 2.0 * Bd * 32.0 * Ed * 2.0 * Ed, 2.0 * Bd * T * Ed + 2.0 * Ed * Ed + 5.0 * Bd * Ed);
+        LaunchScope ls(c, "dec_cross_attention_rc", 2.0 * Bd * (T > 32 ? 64.0 : 32.0) * Ed * 2.0 * Ed,
+                       2.0 * Bd * T * Ed + 2.0 * Ed * Ed + 5.0 * Bd * Ed);
         if (launch_cross_attention_rc(k, c.num_sms, s)) {
           set_error("recompute cross-attention launch failed");
           return 1;

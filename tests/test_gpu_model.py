@@ -69,7 +69,7 @@ def test_forward_ragged_batches(tiny_gpu, shape):
     assert np.array_equal(fused["step_tokens"], ref["step_tokens"]) and fused["target_tokens"] == out["target_tokens"]
 
 
-@pytest.mark.parametrize("shape", [(37, 32), (9, 20), (4, 32)])
+@pytest.mark.parametrize("shape", [(37, 32), (9, 20), (4, 32), (5, 33), (7, 64), (41, 48), (3, 40), (130, 64), (2, 57)])
 def test_cross_attention_recompute_equals_cached_path(tiny_gpu, shape, monkeypatch):
     """S <= 32 batches re-project K/V on the tensor cores every step (cross_attention_rc.cu); forcing the cached
     f32 K/V kernel must give the same bits, and both must equal the oracle."""
