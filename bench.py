@@ -51,6 +51,9 @@ WORKLOADS = {
     "base_shortlist": dict(dims="BASE", shortlist=True, sentences=4096, length=32, max_words=4096 * 32,
                            desc="base int8 (emb 512, ffn 2048, 6 enc / 2 SSRU dec, vocab 32000, random-init) with lexical "
                                 "shortlist, 4096 synthetic sentences x 32 tokens per GPU (BASELINE.json configs[2])"),
+    "tiny_b64": dict(dims="TINY", shortlist=True, sentences=64, length=32, max_words=64 * 32,
+                     desc="tiny11 int8 with lexical shortlist, ONE batch of 64 synthetic sentences x 32 tokens (BASELINE.json "
+                          "configs[0], the reference's CPU-runnable case: the latency regime, two decoder tiles)"),
     "tiny_len64": dict(dims="TINY", shortlist=True, sentences=2048, length=64, max_words=2048 * 64,
                        desc="tiny11 int8 with lexical shortlist, 2048 synthetic sentences x 64 tokens per GPU (the same 131072 "
                             "source tokens as the headline at twice the sentence length: the two-key-block recompute "
