@@ -656,6 +656,16 @@ int model_forward(Model& m, ForwardArgs& a) {
     for (int i = 0; i < 3; i++)
       if (c.make_map(&map_qa[i], qa[i], R, E, 128)) return 1;
 
+  // debugging aid: SLIMT_B200_TRACE=<file> records the phase stamps of the row-tile kernels: the encoder's first FFN
+  // launch (first tile of every CTA) and the two decoder kernels of layer 0 in decode step 3
+  const char* trace_path = getenv("SLIMT_B200_TRACE");
+  long long* trace_buf = nullptr;
+  const size_t trace_n = static_cast<size_t>(c.num_sms) * kTraceSlots;
+  if (trace_path) {
+    SB_CUDA(cudaMallocManaged(&trace_buf, 3 * trace_n * sizeof(long long)));
+    SB_CUDA(cudaMemsetAsync(trace_buf, 0, 3 * trace_n * sizeof(long long), s));
+  }
+
   // ---- embedding (Model.cc:195-197)
   {
     QuantOuts q = qouts();
@@ -729,6 +739,7 @@ int model_forward(Model& m, ForwardArgs& a) {
         k.n_zq = 2 * Ld;
       }
       k.M = R;
+      if (trace_buf && i == 0) k.trace = trace_buf + 2 * trace_n;
       const double Rd = R, Ed = E, Fd = F;
       LaunchScope ls(c, "enc_wo_ffn_fused", 2.0 * Rd * (Ed * Ed + 2.0 * Ed * Fd),
                      Ed * Ed + 2.0 * Ed * Fd + Rd * Ed * (1.0 + 4.0 + 8.0 + 4.0 + k.n_zq));
@@ -906,14 +917,6 @@ int model_forward(Model& m, ForwardArgs& a) {
     launch_embed(nullptr, m.emb_q, m.inv_qm, m.sqrt_e, m.pos, B, 1, E, 0, 1, xd, q, s);
   }
 
-  // debugging aid: SLIMT_B200_TRACE=<file> records the phase stamps of the row-tile kernels of one decode step
-  const char* trace_path = getenv("SLIMT_B200_TRACE");
-  long long* trace_buf = nullptr;
-  const size_t trace_n = static_cast<size_t>(c.num_sms) * kTraceSlots;
-  if (trace_path) {
-    SB_CUDA(cudaMallocManaged(&trace_buf, 2 * trace_n * sizeof(long long)));
-    SB_CUDA(cudaMemsetAsync(trace_buf, 0, 2 * trace_n * sizeof(long long), s));
-  }
   int executed = 0;
   int host_done = 0;
   for (int step = 0; step < max_steps; step++) {
@@ -1059,11 +1062,11 @@ int model_forward(Model& m, ForwardArgs& a) {
   if (trace_buf) {
     SB_CUDA(cudaStreamSynchronize(s));
     if (FILE* f = fopen(trace_path, "w")) {
-      for (int k = 0; k < 2; k++)
+      for (int k = 0; k < 3; k++)
         for (int cta = 0; cta < c.num_sms; cta++) {
           const long long* t = trace_buf + k * trace_n + static_cast<size_t>(cta) * kTraceSlots;
           if (t[0] == 0) continue;
-          fprintf(f, "%s %d", k == 0 ? "ssru" : "ffn", cta);
+          fprintf(f, "%s %d", k == 0 ? "ssru" : k == 1 ? "ffn" : "encffn", cta);
           for (int i = 0; i < kTraceSlots; i++) fprintf(f, " %lld", t[i] ? t[i] - t[0] : -1);
           fprintf(f, "\n");
         }

@@ -12,7 +12,8 @@
 // phase stamp of the calling thread into the CTA's trace slots (no-op unless the launch carries a trace buffer)
 #define SB_TRACE(args, slot)                                                                  \
   do {                                                                                        \
-    if ((args).trace) (args).trace[blockIdx.x * kTraceSlots + (slot)] = clock64();            \
+    if ((args).trace && (args).trace[blockIdx.x * kTraceSlots + (slot)] == 0)                 \
+      (args).trace[blockIdx.x * kTraceSlots + (slot)] = clock64(); /* first tile of the CTA */ \
   } while (0)
 
 namespace sb {

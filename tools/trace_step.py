@@ -51,12 +51,14 @@ def main():
             os.environ["SLIMT_B200_TRACE"] = raw
         model.forward(tok, lens, shortlist=sl)
     os.environ.pop("SLIMT_B200_TRACE")
-    rows = {"ssru": [], "ffn": []}
+    rows = {"ssru": [], "ffn": [], "encffn": []}
     for line in open(raw):
         p = line.split()
         rows[p[0]].append([int(x) for x in p[2:]])
     with open(out_path, "w") as f:
-        for name, names in (("ssru", SSRU), ("ffn", FFN)):
+        for name, names in (("ssru", SSRU), ("ffn", FFN), ("encffn", FFN)):
+            if not rows[name]:
+                continue
             a = np.array(rows[name], dtype=np.float64)
             a[a < 0] = np.nan
             med, lo, hi = np.nanmedian(a, axis=0), np.nanmin(a, axis=0), np.nanmax(a, axis=0)
