@@ -3,5 +3,5 @@
 TAG=${1:-wl}
 for w in tiny_full base_shortlist mixed; do
   timeout 900 python bench.py --workload $w --steps 3 --warmup 3 > gpurun_out/${TAG}_${w}.json 2> gpurun_out/${TAG}_${w}.err
-  echo "== $w"; tail -2 gpurun_out/${TAG}_${w}.err; python tools/bench_summary.py gpurun_out/${TAG}_${w}.json | head -9
+  echo "== $w"; tail -2 gpurun_out/${TAG}_${w}.err; python tools/bench_summary.py gpurun_out/${TAG}_${w}.json 2>/dev/null | head -9
 done
