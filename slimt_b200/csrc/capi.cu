@@ -209,7 +209,7 @@ int slimt_b200_translate(slimt_b200_model* model, slimt_b200_translate_io* io) {
       if (b.empty()) break;
       const size_t max_steps = static_cast<size_t>(io->limit_factor * static_cast<float>(width));
       in_bytes = std::max(in_bytes, 4 * (b.size() * width + b.size()));
-      steps_bytes = std::max(steps_bytes, 4 * std::max<size_t>(1, max_steps) * b.size());
+      steps_bytes = std::max(steps_bytes, 4 * (std::max<size_t>(1, max_steps) + 1) * b.size());
     }
   }
   in_bytes = (in_bytes + 255) & ~size_t(255);
@@ -242,31 +242,29 @@ int slimt_b200_translate(slimt_b200_model* model, slimt_b200_translate_io* io) {
     // while the GPU runs the encoder (the callback fires once the encoder kernels are queued)
     LazyShortlist lazy{&gen, &words, static_cast<size_t>(m.V), {}};
     const size_t max_steps = static_cast<size_t>(io->limit_factor * static_cast<float>(width));
-    uint32_t* steps = reinterpret_cast<uint32_t*>(stage + in_bytes);
+    // one row of up to max_steps tokens per sentence (transposed on the device) followed by the recorded lengths
+    const size_t stride = std::max<size_t>(1, max_steps);
+    uint32_t* rows = reinterpret_cast<uint32_t*>(stage + in_bytes);
+    uint32_t* lens = rows + stride * B;
     sb::ForwardArgs a;
     a.tokens = tokens, a.lengths = lengths, a.B = B, a.T = width;
     a.limit_factor = io->limit_factor;
     if (use_sl) a.shortlist_cb = lazy_shortlist_cb, a.shortlist_user = &lazy;
-    a.step_tokens = steps;
+    a.sentence_tokens = rows, a.row_stride = stride, a.target_lengths = lens;
     if (sb::model_forward(m, a)) {
       cudaEventDestroy(e0), cudaEventDestroy(e1);
       return 1;
     }
     size_t kept_total = 0;
     for (size_t r = 0; r < B; r++) {
-      uint32_t n = 0;
-      while (n < a.steps) {
-        if (steps[n++ * B + r] == 0u) break;
-      }
-      out_len[batch[r]] = n;
-      kept_total += n;
+      out_len[batch[r]] = lens[r];
+      kept_total += lens[r];
     }
     std::vector<uint32_t> kept(kept_total);
     size_t pos = 0;
     for (size_t r = 0; r < B; r++) {
-      const uint32_t n = out_len[batch[r]];
-      for (uint32_t k = 0; k < n; k++) kept[pos + k] = steps[k * B + r];
-      pos += n;
+      memcpy(kept.data() + pos, rows + r * stride, 4ul * lens[r]);
+      pos += lens[r];
     }
     done.push_back(Done{std::move(batch), std::move(kept)});
     io->target_tokens += a.target_tokens;

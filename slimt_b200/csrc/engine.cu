@@ -608,6 +608,7 @@ int model_forward(Model& m, ForwardArgs& a) {
   acc(8ul * B), acc(B), acc(4ul * B), acc(256);                 // best, done, tgt_len, counters
   acc(4ul * std::max(1, max_steps) * B);                        // step tokens
   if (a.forced) acc(4ul * std::max(1, max_steps) * B);
+  if (a.sentence_tokens) acc(4ul * std::max(1, max_steps) * B);
   if (use_sl) acc(4ul * Nout), acc(1ul * Nout * E), acc(4ul * Nout), acc(4ul * Nout), acc(4ul * (Nout / 32 + 1));
   if (a.logits) acc(4ul * B * Nout);
   if (a.alignment) acc(4ul * B * T);
@@ -1082,7 +1083,23 @@ int model_forward(Model& m, ForwardArgs& a) {
     SB_CUDA(cudaMemcpyAsync(a.step_tokens, d_steps, 4ul * executed * B, cudaMemcpyDeviceToHost, s));
     c.d2h_bytes += 4ul * executed * B;
   }
+  if (!a.device_io && a.sentence_tokens && executed > 0) {
+    if (a.row_stride < static_cast<size_t>(executed)) {
+      set_error("sentence_tokens: row_stride smaller than the number of decode steps");
+      return 1;
+    }
+    // one row per sentence: the host then copies each sentence's recorded prefix without striding through the matrix
+    uint32_t* d_rows = c.take<uint32_t>(static_cast<size_t>(std::max(1, max_steps)) * B);
+    {
+      LaunchScope ls(c, "transpose_steps", 0, 8.0 * executed * B);
+      launch_transpose_u32(d_steps, executed, B, d_rows, executed, s);
+    }
+    SB_CUDA(cudaMemcpy2DAsync(a.sentence_tokens, 4ul * a.row_stride, d_rows, 4ul * executed, 4ul * executed, B,
+                              cudaMemcpyDeviceToHost, s));
+    c.d2h_bytes += 4ul * executed * B;
+  }
   SB_CUDA(cudaStreamSynchronize(s));
+  if (a.target_lengths) memcpy(a.target_lengths, lens.data(), 4ul * B);
   c.d2h_bytes += 4ul * B;
   uint64_t total = 0;
   uint32_t longest = 0;

@@ -167,6 +167,12 @@ struct ForwardArgs {
   const uint32_t* forced = nullptr;
   bool device_io = false;
   uint32_t* step_tokens = nullptr;
+  // Host-buffer mode, alternative to step_tokens: the step matrix transposed on the device to one row per sentence,
+  // [B][row_stride] (row_stride >= limit_factor * T), plus each sentence's recorded length (Model.cc:127-137) -- what
+  // the service path's record() needs, contiguous per sentence.
+  uint32_t* sentence_tokens = nullptr;
+  size_t row_stride = 0;
+  uint32_t* target_lengths = nullptr;
   size_t steps = 0;
   uint64_t target_tokens = 0;
   float* encoder_out = nullptr;

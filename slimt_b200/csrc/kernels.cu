@@ -365,6 +365,26 @@ void launch_out_bounds(const int32_t* c127, const float* pb, float um, int N, fl
   out_bounds_kernel<<<(chunks + 7) / 8, 256, 0, stream>>>(c127, pb, um, N, dmax);
 }
 
+__global__ void transpose_u32_kernel(const uint32_t* __restrict__ src, int rows, int cols, uint32_t* __restrict__ dst,
+                                     int dst_stride) {
+  __shared__ uint32_t tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[static_cast<size_t>(r) * cols + c] : 0u;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) dst[static_cast<size_t>(c) * dst_stride + r] = tile[threadIdx.x][i];
+  }
+}
+
+void launch_transpose_u32(const uint32_t* src, int rows, int cols, uint32_t* dst, int dst_stride, cudaStream_t stream) {
+  if (rows == 0 || cols == 0) return;
+  transpose_u32_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, stream>>>(src, rows, cols, dst, dst_stride);
+}
+
 void launch_argmax_rows(const float* logits, int rows, int cols, unsigned long long* best, cudaStream_t stream) {
   if (rows == 0) return;
   argmax_rows_kernel<<<rows, 256, 0, stream>>>(logits, cols, best);
