@@ -243,7 +243,7 @@ void launch_cross_attention(const CUtensorMap& mapK, const CUtensorMap& mapV, co
 #define SB_CA_LAUNCH(DH_, NC_)                                                                                   \
   do {                                                                                                           \
     auto kern = cross_attention_kernel<DH_, 8, NC_>;                                                             \
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));             \
+    ensure_dyn_smem(kern, smem);             \
     kern<<<grid, threads, smem, stream>>>(mapK, mapV, Qr, lengths, B, S, box_rows, stages, dk, out_f32, q,      \
                                           attn_head0);                                                           \
   } while (0)

@@ -451,7 +451,7 @@ int launch_cross_attention_rc(const CrossRcArgs& a, int num_sms, cudaStream_t st
   const int per_group = two ? kGroup / 2 : kGroup;
   const int groups = (a.B + per_group - 1) / per_group;
   auto kern = two ? cross_attention_rc_kernel<2> : cross_attention_rc_kernel<1>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total) != cudaSuccess) return 1;
+  if (ensure_dyn_smem(kern, Smem::total) != cudaSuccess) return 1;
   return launch_pdl(kern, dim3(groups < num_sms ? groups : num_sms), dim3(kThreadsRc), Smem::total, stream, a) != cudaSuccess;
 }
 

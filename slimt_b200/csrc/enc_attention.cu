@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(kThreadsEa, 1) enc_attention_kernel(const __gr
 template <int TMAX>
 int launch_t(const EncAttnArgs& a, int grid, cudaStream_t stream) {
   auto kern = enc_attention_kernel<TMAX>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total) != cudaSuccess) return 1;
+  if (ensure_dyn_smem(kern, Smem::total) != cudaSuccess) return 1;
   return launch_pdl(kern, dim3(grid), dim3(kThreadsEa), Smem::total, stream, a) != cudaSuccess;
 }
 

@@ -240,7 +240,7 @@ template <class Kern, class Args>
 int launch_rows(Kern kern, const Args& a, size_t smem, cudaStream_t stream) {
   const int tiles = (a.M + kR - 1) / kR;
   if (tiles == 0) return 0;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  ensure_dyn_smem(kern, smem);
   int sms = 148;
   int dev = 0;
   cudaGetDevice(&dev);

@@ -299,7 +299,7 @@ void launch_one(const GemmBatch& b, int n_problems, cudaStream_t stream) {
   const size_t smem = gemm_smem_bytes(BN, STAGES);
   auto kern = gemm_i8_kernel<BN, STAGES, EPI>;
   if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    ensure_dyn_smem(kern, smem);
     configured = true;
   }
   dim3 grid((b.N + BN - 1) / BN, (b.M + kBM - 1) / kBM, n_problems);

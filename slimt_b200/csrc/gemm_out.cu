@@ -297,13 +297,13 @@ int launch_gemm_out_argmax(const CUtensorMap& tma_a, const CUtensorMap& tma_b, c
   const size_t smem = out_smem_bytes(KB);
   if (KB == 2) {
     auto kern = out_argmax_kernel<2>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    ensure_dyn_smem(kern, smem);
     if (launch_pdl(kern, dim3(grid), dim3(kOutThreads), smem, stream, tma_a, tma_b, pb, c127, dmax, um, eta, M, N, best) !=
         cudaSuccess)
       return 1;
   } else if (KB == 4) {
     auto kern = out_argmax_kernel<4>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    ensure_dyn_smem(kern, smem);
     if (launch_pdl(kern, dim3(grid), dim3(kOutThreads), smem, stream, tma_a, tma_b, pb, c127, dmax, um, eta, M, N, best) !=
         cudaSuccess)
       return 1;

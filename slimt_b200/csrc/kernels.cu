@@ -326,10 +326,10 @@ void launch_self_attention(const float* Q, const float* K, const float* V, const
     smem = (static_cast<size_t>(2) * T * dh + static_cast<size_t>(threads) * Tp) * sizeof(float);
   }
   if (dh == 32) {
-    cudaFuncSetAttribute(self_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    ensure_dyn_smem(self_attention_kernel<32>, smem);
     self_attention_kernel<32><<<B * H, threads, smem, stream>>>(Q, K, V, lengths, T, H, dk, out_f32, q);
   } else if (dh == 64) {
-    cudaFuncSetAttribute(self_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    ensure_dyn_smem(self_attention_kernel<64>, smem);
     self_attention_kernel<64><<<B * H, threads, smem, stream>>>(Q, K, V, lengths, T, H, dk, out_f32, q);
   } else {
     fprintf(stderr, "slimt_b200: unsupported head dim %d\n", dh);

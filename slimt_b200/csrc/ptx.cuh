@@ -219,8 +219,33 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 }  // namespace sb
 
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 #include <utility>
 namespace sb {
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel, size) instead of before every launch: the
+// call costs 1-2 us of host time and a decode step launches seven kernels.
+template <class Kern>
+inline cudaError_t ensure_dyn_smem(Kern kern, size_t bytes) {
+  static std::mutex mu;
+  static std::unordered_map<unsigned long long, size_t> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long key = (static_cast<unsigned long long>(dev) << 56) ^ reinterpret_cast<unsigned long long>(kern);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = done.find(key);
+    if (it != done.end() && it->second >= bytes) return cudaSuccess;
+  }
+  const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e == cudaSuccess) {
+    std::lock_guard<std::mutex> g(mu);
+    size_t& v = done[key];
+    if (bytes > v) v = bytes;
+  }
+  return e;
+}
 
 // SLIMT_B200_PDL=0 turns the attribute off (plain stream order) for A/B measurements.
 inline bool pdl_enabled() {

@@ -387,7 +387,7 @@ int launch(const RowsFfnArgs& a, cudaStream_t stream) {
   if (tiles == 0) return 0;
   if (L::kParkY && a.y_park == nullptr) return 1;
   auto kern = rows_ffn_kernel<E, F, R>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
+  ensure_dyn_smem(kern, L::total);
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
