@@ -30,7 +30,7 @@ namespace sb {
 namespace {
 
 constexpr int kOutBN = 256;
-constexpr int kOutStages = 6;
+constexpr int kOutStages = 4;  // a power of two: the ring position is a % and a / in the single-thread issue loops (6: +5 us)
 constexpr int kOutThreads = 640;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-19 epilogue
 
 __device__ __forceinline__ unsigned long long pack_best_out(float v, uint32_t idx) {
