@@ -32,6 +32,11 @@
 #include <utility>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "slimt_b200.h"
 
 namespace slimt {
@@ -202,6 +207,55 @@ class Input {
   float limit_factor_;
 };
 
+// ---------------------------------------------------------------- io::MmapFile (slimt/Io.hh, Io.cc:291-340)
+namespace io {
+// Read-only private mapping of a file; move-only; throws std::runtime_error exactly where the reference does.
+class MmapFile {
+ public:
+  MmapFile() = default;
+  explicit MmapFile(const std::string &filepath) {
+    fd_ = open(filepath.c_str(), O_RDONLY);
+    if (fd_ == -1) throw std::runtime_error("Failed to open file: " + filepath);
+    struct stat st;
+    if (fstat(fd_, &st) == -1) {
+      close(fd_);
+      throw std::runtime_error("Failed to get file size: " + filepath);
+    }
+    size_ = static_cast<size_t>(st.st_size);
+    data_ = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0);
+    if (data_ == MAP_FAILED) {
+      close(fd_);
+      throw std::runtime_error("Failed to mmap file: " + filepath);
+    }
+  }
+  ~MmapFile() { release(); }
+  MmapFile(const MmapFile &) = delete;
+  MmapFile &operator=(const MmapFile &) = delete;
+  MmapFile(MmapFile &&from) noexcept : fd_(from.fd_), data_(from.data_), size_(from.size_) { from.reset(); }
+  MmapFile &operator=(MmapFile &&from) noexcept {
+    if (this != &from) {
+      release();
+      fd_ = from.fd_, data_ = from.data_, size_ = from.size_;
+      from.reset();
+    }
+    return *this;
+  }
+  void *data() const { return data_; }
+  size_t size() const { return size_; }
+
+ private:
+  void reset() { fd_ = -1, data_ = nullptr, size_ = 0; }
+  void release() {
+    if (data_ != nullptr && data_ != MAP_FAILED) munmap(data_, size_);
+    if (fd_ != -1) close(fd_);
+    reset();
+  }
+  int fd_ = -1;
+  void *data_ = nullptr;
+  size_t size_ = 0;
+};
+}  // namespace io
+
 // ---------------------------------------------------------------- Model (slimt/Model.hh)
 template <class Field>
 struct Package {
@@ -220,10 +274,37 @@ class Model {
     std::string split_mode = "sentence";
   };
 
+  // Model.hh:53: the files are mapped (io::MmapFile) and stay mapped for the model's lifetime, as in the reference
+  // (Model.cc:52-66); an empty path leaves the field empty.  Throws std::runtime_error for a missing file.
+  Model(const Config &config, const Package<std::string> &package, int device = 0)
+      : Model(config, map_files(package), device, 0) {}
+
   Model(const Config &config, const Package<View> &package, int device = 0) : config_(config), device_(device) {
-    slimt_b200_model_config c{static_cast<int32_t>(config.encoder_layers), static_cast<int32_t>(config.decoder_layers),
-                              static_cast<int32_t>(config.feed_forward_depth), static_cast<int32_t>(config.num_heads)};
-    detail::check(slimt_b200_model_create(detail::context(device), package.model.data, package.model.size, &c, &model_),
+    create(package);
+  }
+  ~Model() { slimt_b200_model_destroy(model_); }
+  Model(const Model &) = delete;
+  Model &operator=(const Model &) = delete;
+
+ private:
+  using Mmap = Package<io::MmapFile>;
+  static Mmap map_files(const Package<std::string> &p) {
+    Mmap m;
+    if (!p.model.empty()) m.model = io::MmapFile(p.model);
+    if (!p.vocabulary.empty()) m.vocabulary = io::MmapFile(p.vocabulary);
+    if (!p.shortlist.empty()) m.shortlist = io::MmapFile(p.shortlist);
+    return m;
+  }
+  Model(const Config &config, Mmap &&files, int device, int /*tag*/)
+      : config_(config), device_(device), mmap_(std::move(files)) {
+    create(Package<View>{{mmap_.model.data(), mmap_.model.size()},
+                         {mmap_.vocabulary.data(), mmap_.vocabulary.size()},
+                         {mmap_.shortlist.data(), mmap_.shortlist.size()}});
+  }
+  void create(const Package<View> &package) {
+    slimt_b200_model_config c{static_cast<int32_t>(config_.encoder_layers), static_cast<int32_t>(config_.decoder_layers),
+                              static_cast<int32_t>(config_.feed_forward_depth), static_cast<int32_t>(config_.num_heads)};
+    detail::check(slimt_b200_model_create(detail::context(device_), package.model.data, package.model.size, &c, &model_),
                   "slimt_b200_model_create");
     int32_t e = 0, f = 0, v = 0;
     slimt_b200_model_dims(model_, &e, &f, &v);
@@ -233,10 +314,8 @@ class Model {
                         static_cast<const char *>(package.shortlist.data) + package.shortlist.size);
     }
   }
-  ~Model() { slimt_b200_model_destroy(model_); }
-  Model(const Model &) = delete;
-  Model &operator=(const Model &) = delete;
 
+ public:
   // Model::forward (Model.cc:187-204): embedding -> encoder -> greedy decode with the per-batch shortlist.
   Histories forward(const Input &input) const {
     const size_t B = input.index(), T = input.indices().dim(-1);
@@ -286,11 +365,19 @@ class Model {
  private:
   Config config_;
   int device_ = 0;
+  Mmap mmap_;  // only used by the path constructor
   slimt_b200_model *model_ = nullptr;
   size_t vocab_ = 0;
   std::vector<char> shortlist_;
   mutable std::mutex mu_;
 };
+
+// Model.hh:85-89, Model.cc:206-245
+namespace preset {
+inline Model::Config tiny() { return Model::Config{6, 2, 2, 8, "sentence"}; }
+inline Model::Config base() { return Model::Config{6, 2, 2, 8, "sentence"}; }
+inline Model::Config nano() { return Model::Config{4, 2, 2, 8, "sentence"}; }
+}  // namespace preset
 
 // ---------------------------------------------------------------- services (slimt/Frontend.hh)
 struct Config {

@@ -42,6 +42,18 @@ int main(int argc, char **argv) {
     }
     std::ofstream out(argv[4], std::ios::binary);
 
+    // 0. host-only pieces: presets (Model.cc:206-245) and the loader's error convention (Io.cc:291-297)
+    if (slimt::preset::nano().encoder_layers != 4 || slimt::preset::tiny().encoder_layers != 6 ||
+        slimt::preset::base().decoder_layers != 2)
+      throw std::runtime_error("preset values");
+    bool threw = false;
+    try {
+      slimt::io::MmapFile missing("/nonexistent/slimt_b200/model.bin");
+    } catch (const std::runtime_error &e) {
+      threw = std::string(e.what()).find("Failed to open file") == 0;
+    }
+    if (!threw) throw std::runtime_error("MmapFile did not report a missing file");
+
     // 1. qmm::affine on Tensors (QMM.hh:48): x [4,64] f32, W {64,16} ig8 as B^T [16][64], bias [1,16]
     slimt::Tensor x(slimt::Type::f32, slimt::Shape({4, 64}), "x");
     slimt::Tensor W(slimt::Type::ig8, slimt::Shape({64, 16}), "W");
@@ -52,9 +64,15 @@ int main(int argc, char **argv) {
     slimt::Tensor y = slimt::qmm::affine(x, W, b, 127.0f / 0.5f, 127.0f / 2.0f, "y");
     put(out, y.data<float>(), 4 * y.size());
 
-    // 2. Model::forward on one Input holding every sentence (Model.cc:187)
-    slimt::Package<slimt::View> package{{model_bin.data(), model_bin.size()}, {nullptr, 0}, {sl_bin.data(), sl_bin.size()}};
-    auto model = std::make_shared<slimt::Model>(slimt::Model::Config{}, package);
+    // 2. Model::forward on one Input holding every sentence (Model.cc:187).  The model comes through the path
+    // constructor (Model.hh:53: files mapped with io::MmapFile), a second one through the View constructor.
+    slimt::Package<std::string> paths{argv[1], "", std::string(argv[2]) == "-" ? "" : argv[2]};
+    auto model = std::make_shared<slimt::Model>(slimt::preset::tiny(), paths);
+    {
+      slimt::Package<slimt::View> package{{model_bin.data(), model_bin.size()}, {nullptr, 0}, {sl_bin.data(), sl_bin.size()}};
+      slimt::Model from_views(slimt::Model::Config{}, package);
+      if (from_views.vocabulary_size() != model->vocabulary_size()) throw std::runtime_error("constructors disagree");
+    }
     slimt::Input input(sources.size(), longest, 0, 1.5f);
     for (const auto &s : sources) input.add(s);
     input.finalize();
