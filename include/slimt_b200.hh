@@ -417,6 +417,13 @@ class Blocking {
     for (size_t i = 0; i < sources.size(); i++) targets[i].assign(out.begin() + out_offsets[i], out.begin() + out_offsets[i + 1]);
     return targets;
   }
+  // Blocking::pivot (Frontend.cc:147-205) on word ids: source -> pivot with `first`, pivot -> target with `second`.
+  // The reference detokenises the pivot text and re-tokenises it with the second model's TextProcessor (text
+  // handling: out of scope here), so at this level the two models must share the pivot-language vocabulary; the
+  // pivot sentences are passed on as produced, EOS included, like the reference's segments (TextProcessor.cc:132-143).
+  Sentences pivot(const Ptr<Model> &first, const Ptr<Model> &second, const Sentences &sources) {
+    return translate(second, translate(first, sources));
+  }
 
  private:
   Config config_;
