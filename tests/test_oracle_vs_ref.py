@@ -105,6 +105,23 @@ def test_forward_bit_exact(tiny_model, shortlist_assets, use_shortlist):
         assert np.array_equal(out["attn"][s], ref["attn"][s]), s
 
 
+def test_forward_long_sentences_bit_exact(tiny_model):
+    """Sentences longer than 32 tokens (positions, softmax rows and decode lengths beyond the short cases above):
+    the restatement still equals the reference bit for bit."""
+    path, items = tiny_model
+    sents = synth.make_sentences(3, (20, 44), seed=57)
+    sents[0] = synth.make_sentences(1, 44, seed=58)[0]
+    tokens, lengths = util.pad_batch(sents)
+    ref = util.ref_forward(path, sents, dump=True)
+    out = so.Oracle(items).forward(tokens, lengths, keep=True)
+    assert np.array_equal(out["encoder_out"], ref["encoder_out"])
+    assert np.array_equal(out["step_tokens"], ref["step_tokens"])
+    assert out["sentences"] == ref["sentences"]
+    for s in range(len(ref["step_tokens"])):
+        assert np.array_equal(out["logits"][s], ref["logits"][s]), s
+        assert np.array_equal(out["attn"][s], ref["attn"][s]), s
+
+
 def test_forward_with_eos_and_teacher_forcing(eos_model):
     path, items = eos_model
     sents = synth.make_sentences(8, (4, 10), seed=33)
