@@ -122,6 +122,23 @@ def test_forward_long_sentences_bit_exact(tiny_model):
         assert np.array_equal(out["attn"][s], ref["attn"][s]), s
 
 
+def test_forward_base_shaped_bit_exact(tmp_path):
+    """BASELINE configs[2] shapes (emb 512, ffn 2048, head size 64): restatement == reference."""
+    path = str(tmp_path / "base.bin")
+    dims = synth.ModelDims(emb=512, ffn=2048, vocab=8000)
+    synth.write_model(path, synth.make_params(dims, seed=5))
+    items = synth.read_model(path)
+    sents = synth.make_sentences(4, (2, 10), vocab=8000, seed=6)
+    tokens, lengths = util.pad_batch(sents)
+    ref = util.ref_forward(path, sents, dump=True)
+    out = so.Oracle(items).forward(tokens, lengths, keep=True)
+    assert np.array_equal(out["encoder_out"], ref["encoder_out"])
+    assert np.array_equal(out["step_tokens"], ref["step_tokens"])
+    for s in range(len(ref["step_tokens"])):
+        assert np.array_equal(out["logits"][s], ref["logits"][s]), s
+        assert np.array_equal(out["attn"][s], ref["attn"][s]), s
+
+
 def test_forward_with_eos_and_teacher_forcing(eos_model):
     path, items = eos_model
     sents = synth.make_sentences(8, (4, 10), seed=33)
