@@ -80,10 +80,15 @@ FORWARD_CASES = {
     "shortlist": (dict(seed=1234), dict(n=5, length=(2, 8), seed=22), True, None),
     "eos": (dict(seed=4321, eos_bias=4.8), dict(n=8, length=(4, 10), seed=33), False, None),
     "forced": (dict(seed=1234), dict(n=3, length=(5, 7), seed=23), False, 4),
+    # sentences of 33-50 tokens: positions past 32, the two-key-block recompute cross-attention, T = 64 encoder attention
+    "long": (dict(seed=1234), dict(n=3, length=(33, 50), seed=24), False, None),
 }
 
 if __name__ == "__main__":
     assert util.have_ref(), "build oracle/_ref first (make -C oracle ref)"
+    only = sys.argv[1:]  # optional: regenerate just the named forward cases
     for name, (pk, sk, sl, fs) in FORWARD_CASES.items():
-        forward_case(name, pk, sk, sl, fs)
-    qmm_cases()
+        if not only or name in only:
+            forward_case(name, pk, sk, sl, fs)
+    if not only:
+        qmm_cases()
