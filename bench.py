@@ -96,7 +96,7 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "10",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -146,11 +146,34 @@ def build_assets(tmp: str, rank: int):
     return model_path, sl_path, (fr, offs, lists), sentences
 
 
-def cpu_reference_run(model_path, shortlist, sentences, workers, batch_sentences=64, repeats=1):
-    """Times oracle/_ref/slimt_ref (the unmodified reference, intgemm provider) on `workers` host threads."""
+def host_isa():
+    """What intgemm's RealCPUID (intgemm.cc:40-86) will find on this host: INTGEMM_CPUID requests are capped to it."""
+    try:
+        flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags")).split()
+    except (OSError, StopIteration):
+        return "unknown"
+    for name, flag in (("AVX512VNNI", "avx512_vnni"), ("AVX512BW", "avx512bw"), ("AVX2", "avx2"), ("SSSE3", "ssse3")):
+        if flag in flags:
+            return name
+    return "SSE2"
+
+
+def cpu_sample(sentences, cores):
+    """A bounded sample of the workload for the CPU arm: one batch per host thread, sized so a pass takes seconds.
+    Returns (sentences, sentences per batch)."""
+    long_ones = not isinstance(WL["length"], int) or WL["length"] > 64
+    per_batch = 8 if long_ones else 64
+    n = min(len(sentences), per_batch * cores)
+    return sentences[:n], per_batch
+
+
+def cpu_reference_run(model_path, shortlist, sentences, workers, batch_sentences=64, repeats=1, isa=None, want_tokens=False):
+    """Times oracle/_ref/slimt_ref (the unmodified reference, intgemm provider) on `workers` host threads.  `isa`
+    sets INTGEMM_CPUID (intgemm.cc:90-108): AVX512VNNI = exact int32 accumulation, AVX512BW = the maddubs path with
+    int16 pair saturation, the arithmetic of slimt's default gemmology provider."""
     from oracle import slimt_oracle as so
     fr, offs, lists = shortlist
-    nb = max(1, len(sentences) // batch_sentences)
+    nb = max(1, (len(sentences) + batch_sentences - 1) // batch_sentences)
     recs = []
     for b in range(nb):
         chunk = sentences[b * batch_sentences:(b + 1) * batch_sentences]
@@ -160,13 +183,64 @@ def cpu_reference_run(model_path, shortlist, sentences, workers, batch_sentences
     with tempfile.NamedTemporaryFile(suffix=".batches", delete=False) as f:
         f.write(np.uint32(len(recs)).tobytes() + b"".join(recs))
         path = f.name
+    tok_path = path + ".tokens"
+    env = dict(os.environ)
+    if isa:
+        env["INTGEMM_CPUID"] = isa
     try:
-        out = subprocess.run([REF_BIN, "bench", "--model", model_path, "--batches", path, "--workers", str(workers),
-                              "--repeat", str(repeats)], capture_output=True, text=True, check=True).stdout
+        cmd = [REF_BIN, "bench", "--model", model_path, "--batches", path, "--workers", str(workers), "--repeat", str(repeats)]
+        if want_tokens:
+            cmd += ["--tokens-out", tok_path]
+        out = subprocess.run(cmd, capture_output=True, text=True, check=True, env=env).stdout
+        tokens = None
+        if want_tokens:
+            flat = np.fromfile(tok_path, dtype=np.uint32)
+            tokens, p = [], 1
+            for _ in range(int(flat[0])):
+                nbs = int(flat[p])
+                p += 1
+                for _ in range(nbs):
+                    n = int(flat[p])
+                    tokens.append(flat[p + 1:p + 1 + n])
+                    p += 1 + n
     finally:
         os.unlink(path)
+        if os.path.exists(tok_path):
+            os.unlink(tok_path)
     lines = [json.loads(l) for l in out.strip().splitlines()]
-    return lines
+    return (lines, tokens) if want_tokens else lines
+
+
+def cpu_baseline_block(model_path, shortlist, sentences, repeats=2):
+    """cpu_baseline of the bench line: the reference on all host threads, on a bounded sample, for both intgemm code
+    paths BASELINE.md section 4.4 asks for.  The headline row is the exact one (VNNI when the host has it)."""
+    cores = os.cpu_count() or 1
+    sample, per_batch = cpu_sample(sentences, cores)
+    rows, toks = [], {}
+    for isa in ("AVX512VNNI", "AVX512BW"):
+        lines, tokens = cpu_reference_run(model_path, shortlist, sample, cores, per_batch, repeats, isa=isa, want_tokens=True)
+        best = max(lines, key=lambda l: l["target_tokens_per_s"])
+        rows.append({"isa_requested": isa, "value": best["target_tokens_per_s"], "unit": "tokens/s",
+                     "seconds": best["seconds"], "target_tokens": best["target_tokens"]})
+        toks[isa] = tokens
+    a, b = toks["AVX512VNNI"], toks["AVX512BW"]
+    same_sent = sum(1 for x, y in zip(a, b) if len(x) == len(y) and np.array_equal(x, y))
+    same_tok = sum(int((x[:min(len(x), len(y))] == y[:min(len(x), len(y))]).sum()) for x, y in zip(a, b))
+    all_tok = sum(max(len(x), len(y)) for x, y in zip(a, b))
+    lens = WL["length"] if isinstance(WL["length"], int) else f"{WL['length'][0]}-{WL['length'][1]}"
+    return {
+        "value": rows[0]["value"], "unit": "tokens/s", "cores": cores, "kind": "reference",
+        "sample": f"{len(sample)} of {WL['sentences']} sentences (lengths {lens}) in {per_batch}-sentence batches"
+                  f"{' each with its own shortlist union' if WL['shortlist'] else ''}, one batch per host thread, best of "
+                  f"{repeats}; oracle/_ref = the unmodified reference compiled in place, intgemm provider + ruy sgemm "
+                  f"(gemmology needs xsimd: unbuildable offline)",
+        "host_isa": host_isa(),
+        "rows": rows,
+        "saturation": {"note": "AVX512BW = maddubs with int16 pair saturation (gemmology-equivalent arithmetic) against "
+                               "AVX512VNNI = exact int32 accumulation (what the GPU computes); requests above host_isa are capped",
+                       "sentences_identical": same_sent, "sentences": len(a),
+                       "token_agreement": round(same_tok / max(1, all_tok), 6)},
+    }
 
 
 def run_reference_arm(args):
@@ -179,19 +253,26 @@ def run_reference_arm(args):
     if not os.path.exists(REF_BIN):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/slimt_ref not built (needs /root/reference)"}))
         return 0
-    # Each step is a bounded sample of the workload: one 64-sentence batch per host thread.
-    sample = sentences[:64 * cores]
-    lines = cpu_reference_run(model_path, shortlist, sample, cores, repeats=args.warmup + args.steps)
+    # Each step is a bounded sample of the workload: one batch per host thread (the reference's Async model,
+    # Frontend.cc:207-227: `workers` threads, each running Model::forward on its own batch).
+    sample, per_batch = cpu_sample(sentences, cores)
+    lines = cpu_reference_run(model_path, shortlist, sample, cores, per_batch, repeats=args.warmup + args.steps)
     timed = lines[args.warmup:]
     secs = sum(l["seconds"] for l in timed)
     toks = sum(l["target_tokens"] for l in timed)
     value = toks / secs
-    sample_desc = f"{len(sample)} of {WL['sentences']} sentences (lengths {WL['length']}) per step, 64-sentence batches, one per thread"
+    lens = WL["length"] if isinstance(WL["length"], int) else f"{WL['length'][0]}-{WL['length'][1]}"
+    sample_desc = (f"{len(sample)} of {WL['sentences']} sentences (lengths {lens}) per step in {per_batch}-sentence batches"
+                   f"{', each with its own shortlist union (smaller than the GPU arm\'s whole-batch union)' if WL['shortlist'] else ''}"
+                   f", one batch per host thread; intgemm provider (host ISA {host_isa()}), ruy sgemm")
+    cfg = workload_config()
+    cfg["reference_batching"] = {"sentences_per_batch": per_batch, "batches_per_step": (len(sample) + per_batch - 1) // per_batch,
+                                 "threads": cores}
     print(json.dumps({
         "impl": "reference", "metric": "target_tokens_per_sec", "value": value, "unit": "tokens/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(timed)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-        "config": workload_config(),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cores, "kind": "reference", "sample": sample_desc},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -207,7 +288,8 @@ def workload_config():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=150,
+                    help="timed passes; the default keeps the timed region above 2 s at the headline size")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -402,29 +484,23 @@ def main():
         "batches_per_step": len(resident),
     }
 
-    if not args.no_cpu_baseline and args.workload in ("tiny_shortlist", "tiny_full"):
-        cores = os.cpu_count() or 1
+    if not args.no_cpu_baseline:
         if os.path.exists(REF_BIN):
-            sample = sentences[:64 * cores]
-            lines = cpu_reference_run(model_path, shortlist, sample, cores, repeats=2)
-            best = max(l["target_tokens_per_s"] for l in lines)
-            out["cpu_baseline"] = {"value": best, "unit": "tokens/s", "cores": cores, "kind": "reference",
-                                   "sample": f"{len(sample)} of {WL['sentences']} sentences x {SRC_LEN} tokens, 64-sentence "
-                                             f"batches, one per host thread (intgemm provider, ruy sgemm), best of 2"}
+            out["cpu_baseline"] = cpu_baseline_block(model_path, shortlist, sentences)
         else:
             from oracle import slimt_oracle as so
             fr, offs, lists = shortlist
             chunk = sentences[:16]
-            tok = np.zeros((16, SRC_LEN), dtype=np.uint32)
+            tok = np.zeros((16, max(len(s) for s in chunk)), dtype=np.uint32)
             for i, s in enumerate(chunk):
                 tok[i, :len(s)] = s
-            sl = so.shortlist_generate(np.concatenate(chunk), fr, offs, lists, synth.TINY.vocab) if WL["shortlist"] else None
+            sl = so.shortlist_generate(np.concatenate(chunk), fr, offs, lists, wl_dims().vocab) if WL["shortlist"] else None
             orc = so.Oracle(synth.read_model(model_path))
             t0 = time.perf_counter()
             res = orc.forward(tok, np.array([len(s) for s in chunk]), LIMIT, shortlist=sl)
             dt = time.perf_counter() - t0
             out["cpu_baseline"] = {"value": sum(len(s) for s in res["sentences"]) / dt, "unit": "tokens/s", "cores": 1,
-                                   "kind": "port", "sample": "16 sentences x 32 tokens through oracle/slimt_oracle.py"}
+                                   "kind": "port", "sample": "16 sentences through oracle/slimt_oracle.py (oracle/_ref not built)"}
     os.write(json_fd, (json.dumps(out) + "\n").encode())
     return 0
 

@@ -78,6 +78,8 @@ typedef struct slimt_b200_model_config {
   int32_t decoder_layers;
   int32_t feed_forward_depth; /* must be 2 */
   int32_t num_heads;
+  uint32_t eos_id;            /* Vocabulary::eos_id() (Vocabulary.hh:22): ends a sentence in record() (Model.cc:127-137) */
+  uint32_t pad_id;            /* Vocabulary::pad_id() (Vocabulary.hh:23): fills the padded batch (Input.cc:20-47) */
 } slimt_b200_model_config;
 
 /* Transformer::Transformer (Transformer.cc:87-94) + io::load_items (Io.cc:114-273):
@@ -94,7 +96,8 @@ typedef struct slimt_b200_forward_io {
   const uint32_t* lengths;  /* [B] */
   size_t batch;             /* B */
   size_t seq;               /* T */
-  float limit_factor;       /* Input::limit_factor(); max steps = (size_t)(limit_factor * T) */
+  float limit_factor;       /* Input::limit_factor(); max steps = max(1, (size_t)(limit_factor * T)): the first decoder
+                               step is unconditional (Model.cc:145-157) */
   const uint32_t* shortlist; /* Shortlist::words() (sorted, size % 8 == 0) or NULL */
   size_t n_shortlist;
   const uint32_t* forced;   /* optional teacher forcing [max_steps][B]; NULL = greedy feedback */
@@ -126,10 +129,19 @@ typedef struct slimt_b200_translate_io {
   float limit_factor;        /* Config::tgt_length_limit_factor */
   const void* shortlist_bin; /* lex.s2t.bin image (Shortlist.hh:78-85) or NULL */
   size_t shortlist_bytes;
+  int32_t shortlist_check;   /* ShortlistGenerator's `check` (Shortlist.hh:52): verify checksum and contents at load.
+                                Whatever its value, a corrupt image is an error, never an out-of-bounds access */
+  int32_t shortlist_shared;  /* ShortlistGenerator's `shared` (Shortlist.cc:132-134): source words are candidates too */
   /* outputs: target sentences, ragged; capacity given by caller */
   uint32_t* out_tokens;
   size_t out_capacity;
   uint64_t* out_offsets;     /* [n_sentences + 1] */
+  /* optional: Response.alignments (Model.cc:84-108, Response.hh): for sentence i, for each of its target tokens, head
+   * 0 of the last decoder layer's cross-attention over the sentence's own source tokens.  Ragged: sentence i owns
+   * out_alignments[out_align_offsets[i] .. out_align_offsets[i + 1]) = [target_len_i][source_len_i] floats. */
+  float* out_alignments;     /* NULL = not wanted */
+  size_t align_capacity;     /* floats */
+  uint64_t* out_align_offsets; /* [n_sentences + 1] */
   uint64_t target_tokens;    /* out */
   uint64_t batches;          /* out */
   double device_ms;          /* out: CUDA-event time of all forward passes on the context's stream */
@@ -140,10 +152,19 @@ typedef struct slimt_b200_translate_io {
 
 int slimt_b200_translate(slimt_b200_model* model, slimt_b200_translate_io* io);
 
+/* The same request served by several replicas of one model (one per GPU, or several on one GPU) from ONE process:
+ * one Batcher forms the batches, and every replica's worker thread takes the next unserved batch as soon as it is
+ * free -- Async's workers pulling from the batcher queue (Frontend.cc:207-227, Batcher.hh:203-259).  Sentences are
+ * independent and every batch is the one the Batcher would have formed anyway, so the output is identical to
+ * slimt_b200_translate's; there is no collective on the data path.  device_ms = the longest replica's time. */
+int slimt_b200_translate_multi(slimt_b200_model* const* replicas, size_t n_replicas, slimt_b200_translate_io* io);
+
 /* Host-only pieces of the same path, callable without a GPU (used by the CPU test-suite):
  * ShortlistGenerator::generate (Shortlist.cc:115-175) and Batcher::generate (Batcher.cc:95-120). */
 int slimt_b200_shortlist_generate(const void* shortlist_bin, size_t shortlist_bytes, const uint32_t* words,
                                   size_t n_words, size_t vocab, uint32_t* out, size_t out_capacity, size_t* n_out);
+/* ShortlistGenerator::load with check = true (Shortlist.cc:41-98, 16-37): header, size, checksum, content_check. */
+int slimt_b200_shortlist_check(const void* shortlist_bin, size_t shortlist_bytes, size_t vocab);
 /* Writes sentence ids batch by batch into batch_ids [n] and the batch boundaries into
  * batch_offsets [n_batches + 1] (capacity n + 1); widths [n_batches] receives each padded length. */
 int slimt_b200_batcher_plan(const uint64_t* lengths, size_t n, size_t max_words, uint64_t* batch_ids,

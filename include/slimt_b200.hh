@@ -7,6 +7,7 @@
 //   slimt::Input                            slimt/Input.hh:10-37     (padded batch of word ids)
 //   slimt::Model::forward -> Histories      slimt/Model.hh:31-83, Model.cc:187-204
 //   slimt::Config, slimt::Blocking, slimt::Async   slimt/Frontend.hh:21-78
+//   slimt::Options, slimt::Response, combine()     slimt/Response.hh:20-58, Response.cc:126-175
 //
 // Everything above Model::forward in the reference works on text (TextProcessor, Vocabulary, Response,
 // Annotation, HTML): those stay the reference's own code and are out of scope here, so the services below
@@ -63,7 +64,9 @@ namespace detail {
 inline void check(int rc, const char *what) {
   if (rc != 0) throw std::runtime_error(std::string(what) + ": " + slimt_b200_last_error());
 }
-// one context per device, created on first use and kept for the life of the process
+// one context per device, created on first use and kept for the life of the process.  Every C-ABI call that uses a
+// context's stream or workspace takes the context's own lock, so models, services and qmm:: calls that share a device
+// serialise on it instead of racing (the reference's callers are re-entrant: Frontend.cc:213-225).
 inline slimt_b200_ctx *context(int device = 0) {
   static std::mutex mu;
   static std::vector<slimt_b200_ctx *> ctxs;
@@ -272,17 +275,26 @@ class Model {
     size_t feed_forward_depth = 2;
     size_t num_heads = 8;
     std::string split_mode = "sentence";
+    // Vocabulary::eos_id() / pad_id() (Vocabulary.hh:22-23) of the model's sentencepiece vocabulary, which stays with
+    // the reference's text front half: the ids are all this path needs from it.
+    uint32_t eos_id = 0;
+    uint32_t pad_id = 0;
   };
 
   // Model.hh:53: the files are mapped (io::MmapFile) and stay mapped for the model's lifetime, as in the reference
   // (Model.cc:52-66); an empty path leaves the field empty.  Throws std::runtime_error for a missing file.
-  Model(const Config &config, const Package<std::string> &package, int device = 0)
-      : Model(config, map_files(package), device, 0) {}
+  // `devices`: one weight replica per listed GPU.  Model::forward uses the first; the services deal batches to all of
+  // them (the reference's Async workers share one Model on the CPU, Frontend.cc:213-225).
+  Model(const Config &config, const Package<std::string> &package, std::vector<int> devices = {0})
+      : Model(config, map_files(package), std::move(devices), 0) {}
 
-  Model(const Config &config, const Package<View> &package, int device = 0) : config_(config), device_(device) {
+  Model(const Config &config, const Package<View> &package, std::vector<int> devices = {0})
+      : config_(config), devices_(std::move(devices)) {
     create(package);
   }
-  ~Model() { slimt_b200_model_destroy(model_); }
+  ~Model() {
+    for (slimt_b200_model *m : replicas_) slimt_b200_model_destroy(m);
+  }
   Model(const Model &) = delete;
   Model &operator=(const Model &) = delete;
 
@@ -295,19 +307,25 @@ class Model {
     if (!p.shortlist.empty()) m.shortlist = io::MmapFile(p.shortlist);
     return m;
   }
-  Model(const Config &config, Mmap &&files, int device, int /*tag*/)
-      : config_(config), device_(device), mmap_(std::move(files)) {
+  Model(const Config &config, Mmap &&files, std::vector<int> devices, int /*tag*/)
+      : config_(config), devices_(std::move(devices)), mmap_(std::move(files)) {
     create(Package<View>{{mmap_.model.data(), mmap_.model.size()},
                          {mmap_.vocabulary.data(), mmap_.vocabulary.size()},
                          {mmap_.shortlist.data(), mmap_.shortlist.size()}});
   }
   void create(const Package<View> &package) {
+    if (devices_.empty()) throw std::runtime_error("Model: at least one device is required");
     slimt_b200_model_config c{static_cast<int32_t>(config_.encoder_layers), static_cast<int32_t>(config_.decoder_layers),
-                              static_cast<int32_t>(config_.feed_forward_depth), static_cast<int32_t>(config_.num_heads)};
-    detail::check(slimt_b200_model_create(detail::context(device_), package.model.data, package.model.size, &c, &model_),
-                  "slimt_b200_model_create");
+                              static_cast<int32_t>(config_.feed_forward_depth), static_cast<int32_t>(config_.num_heads),
+                              config_.eos_id, config_.pad_id};
+    for (int device : devices_) {
+      slimt_b200_model *m = nullptr;
+      detail::check(slimt_b200_model_create(detail::context(device), package.model.data, package.model.size, &c, &m),
+                    "slimt_b200_model_create");
+      replicas_.push_back(m);
+    }
     int32_t e = 0, f = 0, v = 0;
-    slimt_b200_model_dims(model_, &e, &f, &v);
+    slimt_b200_model_dims(replicas_[0], &e, &f, &v);
     vocab_ = static_cast<size_t>(v);
     if (package.shortlist.data != nullptr && package.shortlist.size > 0) {
       shortlist_.assign(static_cast<const char *>(package.shortlist.data),
@@ -317,6 +335,8 @@ class Model {
 
  public:
   // Model::forward (Model.cc:187-204): embedding -> encoder -> greedy decode with the per-batch shortlist.
+  // Re-entrant like the reference's: concurrent calls serialise on the device context's own lock (one stream and one
+  // workspace per context), not on this object.
   Histories forward(const Input &input) const {
     const size_t B = input.index(), T = input.indices().dim(-1);
     std::vector<uint32_t> lengths(input.lengths().begin(), input.lengths().end());
@@ -329,8 +349,9 @@ class Model {
                     "slimt_b200_shortlist_generate");
       shortlist.resize(n);
     }
-    const size_t max_steps = static_cast<size_t>(input.limit_factor() * static_cast<float>(T));
-    std::vector<uint32_t> steps(std::max<size_t>(1, max_steps) * std::max<size_t>(1, B));
+    // the first decoder step is unconditional (Model.cc:145-157): at least one step
+    const size_t max_steps = std::max<size_t>(1, static_cast<size_t>(input.limit_factor() * static_cast<float>(T)));
+    std::vector<uint32_t> steps(max_steps * std::max<size_t>(1, B));
     std::vector<float> align(steps.size() * T);
     slimt_b200_forward_io io;
     std::memset(&io, 0, sizeof(io));
@@ -338,10 +359,7 @@ class Model {
     io.limit_factor = input.limit_factor();
     io.shortlist = shortlist.empty() ? nullptr : shortlist.data(), io.n_shortlist = shortlist.size();
     io.step_tokens = steps.data(), io.alignment = align.data();
-    {
-      std::lock_guard<std::mutex> lock(mu_);  // one stream and workspace per context: forward calls are serialised
-      detail::check(slimt_b200_model_forward(model_, &io), "slimt_b200_model_forward");
-    }
+    detail::check(slimt_b200_model_forward(replicas_[0], &io), "slimt_b200_model_forward");
     Histories histories;
     for (size_t b = 0; b < B; b++) {  // record() + update_alignment (Model.cc:84-137)
       auto h = std::make_shared<Hypothesis>();
@@ -350,7 +368,7 @@ class Model {
         h->target.push_back(w);
         const float *row = align.data() + (s * B + b) * T;
         h->alignment.emplace_back(row, row + lengths[b]);
-        if (w == 0u) break;  // eos id
+        if (w == config_.eos_id) break;
       }
       histories.push_back(std::move(h));
     }
@@ -358,18 +376,18 @@ class Model {
   }
   const Config &config() const { return config_; }
   size_t vocabulary_size() const { return vocab_; }
-  int device() const { return device_; }
-  slimt_b200_model *handle() const { return model_; }
+  const std::vector<int> &devices() const { return devices_; }
+  slimt_b200_model *handle() const { return replicas_[0]; }
+  const std::vector<slimt_b200_model *> &replicas() const { return replicas_; }
   const std::vector<char> &shortlist_image() const { return shortlist_; }
 
  private:
   Config config_;
-  int device_ = 0;
+  std::vector<int> devices_;
   Mmap mmap_;  // only used by the path constructor
-  slimt_b200_model *model_ = nullptr;
+  std::vector<slimt_b200_model *> replicas_;
   size_t vocab_ = 0;
   std::vector<char> shortlist_;
-  mutable std::mutex mu_;
 };
 
 // Model.hh:85-89, Model.cc:206-245
@@ -379,7 +397,7 @@ inline Model::Config base() { return Model::Config{6, 2, 2, 8, "sentence"}; }
 inline Model::Config nano() { return Model::Config{4, 2, 2, 8, "sentence"}; }
 }  // namespace preset
 
-// ---------------------------------------------------------------- services (slimt/Frontend.hh)
+// ---------------------------------------------------------------- services (slimt/Frontend.hh, slimt/Response.hh)
 struct Config {
   size_t max_words = 1024;
   size_t cache_size = 1024;
@@ -388,12 +406,50 @@ struct Config {
   size_t wrap_length = 128;
 };
 
-// Blocking::translate (Frontend.cc:91-145 + exhaust() :42-60) on word ids: Batcher, per-batch shortlist,
-// Model::forward per batch, all inside one C-ABI call.
+// Response.hh:45-48
+struct Options {
+  bool alignment = false;  // include alignments or not
+  bool html = false;       // text handling: not on this path, ignored
+};
+
+// Response (Response.hh:20-43) at the level this path works on: the reference's AnnotatedText source / target become
+// the sentences' word ids; alignments[i][t][s] = p(source token s | target token t) of sentence i (head 0 of the last
+// decoder layer's cross-attention, Model.cc:84-108), empty unless Options::alignment.
+struct Response {
+  Sentences source;
+  Sentences target;
+  std::vector<Alignment> alignments;
+  size_t size() const { return source.size(); }
+};
+
+// remap_alignments + combine (Response.cc:126-175) for pivoting.  On word ids the pivot sentence is handed to the second
+// model as produced, so the character-overlap transfer between two tokenisations of the pivot text is the identity and
+// what remains is the marginalisation p(s | t) = sum_q p(s | q) p(q | t).
+inline Response combine(Response &&first, Response &&second) {
+  Response out;
+  if (!first.alignments.empty() && !second.alignments.empty()) {
+    for (size_t i = 0; i < first.source.size(); i++) {
+      const Alignment &s_given_q = first.alignments[i];
+      const Alignment &q_given_t = second.alignments[i];
+      const size_t S = first.source[i].size(), Q = s_given_q.size();
+      Alignment a(q_given_t.size(), Distribution(S, 0.0F));
+      for (size_t t = 0; t < q_given_t.size(); t++)
+        for (size_t q = 0; q < Q && q < q_given_t[t].size(); q++)
+          for (size_t src = 0; src < S; src++) a[t][src] += s_given_q[q][src] * q_given_t[t][q];
+      out.alignments.push_back(std::move(a));
+    }
+  }
+  out.source = std::move(first.source);
+  out.target = std::move(second.target);
+  return out;
+}
+
+// Blocking::translate (Frontend.cc:91-145 + exhaust() :42-60) on word ids: one Batcher, per-batch shortlist,
+// Model::forward per batch -- dealt to every replica of the model -- all inside one C-ABI call.
 class Blocking {
  public:
   explicit Blocking(const Config &config) : config_(config) {}
-  Sentences translate(const Ptr<Model> &model, const Sentences &sources) {
+  Response translate(const Ptr<Model> &model, const Sentences &sources, const Options &options = Options()) {
     std::vector<uint32_t> tokens;
     std::vector<uint64_t> offsets(1, 0);
     size_t longest = 0;
@@ -402,9 +458,11 @@ class Blocking {
       offsets.push_back(tokens.size());
       longest = std::max(longest, s.size());
     }
-    const size_t per = static_cast<size_t>(config_.tgt_length_limit_factor * static_cast<float>(longest)) + 1;
+    const size_t per = std::max<size_t>(1, static_cast<size_t>(config_.tgt_length_limit_factor * static_cast<float>(longest)));
     std::vector<uint32_t> out(std::max<size_t>(1, per * sources.size()));
     std::vector<uint64_t> out_offsets(sources.size() + 1, 0);
+    std::vector<float> align;
+    std::vector<uint64_t> align_offsets(sources.size() + 1, 0);
     slimt_b200_translate_io io;
     std::memset(&io, 0, sizeof(io));
     io.tokens = tokens.data(), io.offsets = offsets.data(), io.n_sentences = sources.size();
@@ -412,30 +470,49 @@ class Blocking {
     const std::vector<char> &sl = model->shortlist_image();
     io.shortlist_bin = sl.empty() ? nullptr : sl.data(), io.shortlist_bytes = sl.size();
     io.out_tokens = out.data(), io.out_capacity = out.size(), io.out_offsets = out_offsets.data();
-    detail::check(slimt_b200_translate(model->handle(), &io), "slimt_b200_translate");
-    Sentences targets(sources.size());
-    for (size_t i = 0; i < sources.size(); i++) targets[i].assign(out.begin() + out_offsets[i], out.begin() + out_offsets[i + 1]);
-    return targets;
+    if (options.alignment) {
+      align.resize(std::max<size_t>(1, per * tokens.size()));
+      io.out_alignments = align.data(), io.align_capacity = align.size(), io.out_align_offsets = align_offsets.data();
+    }
+    const std::vector<slimt_b200_model *> &replicas = model->replicas();
+    detail::check(slimt_b200_translate_multi(replicas.data(), replicas.size(), &io), "slimt_b200_translate_multi");
+    Response response;
+    response.source = sources;
+    response.target.resize(sources.size());
+    for (size_t i = 0; i < sources.size(); i++)
+      response.target[i].assign(out.begin() + out_offsets[i], out.begin() + out_offsets[i + 1]);
+    if (options.alignment) {
+      response.alignments.resize(sources.size());
+      for (size_t i = 0; i < sources.size(); i++) {
+        const size_t S = sources[i].size();
+        const float *p = align.data() + align_offsets[i];
+        for (size_t t = 0; t < response.target[i].size(); t++) response.alignments[i].emplace_back(p + t * S, p + (t + 1) * S);
+      }
+    }
+    return response;
   }
   // Blocking::pivot (Frontend.cc:147-205) on word ids: source -> pivot with `first`, pivot -> target with `second`.
   // The reference detokenises the pivot text and re-tokenises it with the second model's TextProcessor (text
   // handling: out of scope here), so at this level the two models must share the pivot-language vocabulary; the
   // pivot sentences are passed on as produced, EOS included, like the reference's segments (TextProcessor.cc:132-143).
-  Sentences pivot(const Ptr<Model> &first, const Ptr<Model> &second, const Sentences &sources) {
-    return translate(second, translate(first, sources));
+  Response pivot(const Ptr<Model> &first, const Ptr<Model> &second, const Sentences &sources,
+                 const Options &options = Options()) {
+    Response source_to_pivot = translate(first, sources, options);
+    Response pivot_to_target = translate(second, source_to_pivot.target, options);
+    return combine(std::move(source_to_pivot), std::move(pivot_to_target));
   }
 
  private:
   Config config_;
 };
 
-// Async (Frontend.cc:207-323): `workers` threads pull requests from one queue and answer through futures.
-// With one Model replica per GPU (models[i] lives on device i) this is the multi-GPU service: sentences are
-// independent, replicas share nothing, no collective is involved.
+// Async (Frontend.cc:207-323): `workers` threads take requests from one queue and answer through futures.  A request
+// is served by Blocking's path, i.e. its batches are dealt to every GPU replica of its model; requests in flight at
+// the same time share the replicas (each device context serialises the batches it is given).
 class Async {
  public:
-  Async(const Config &config, std::vector<Ptr<Model>> replicas) : config_(config), replicas_(std::move(replicas)) {
-    for (const Ptr<Model> &m : replicas_) workers_.emplace_back([this, m]() { work(m); });
+  explicit Async(const Config &config) : config_(config) {
+    for (size_t i = 0; i < std::max<size_t>(1, config_.workers); i++) workers_.emplace_back([this]() { work(); });
   }
   ~Async() {
     {
@@ -445,10 +522,24 @@ class Async {
     cv_.notify_all();
     for (std::thread &t : workers_) t.join();
   }
-  std::future<Sentences> translate(Sentences sources) {
-    Job job;
-    job.sources = std::move(sources);
-    std::future<Sentences> f = job.promise.get_future();
+  std::future<Response> translate(const Ptr<Model> &model, Sentences sources, const Options &options = Options()) {
+    return enqueue(Job{model, nullptr, std::move(sources), options, {}});
+  }
+  // Async::pivot (Frontend.cc:259-314): the second translation is chained behind the first inside the worker
+  std::future<Response> pivot(const Ptr<Model> &first, const Ptr<Model> &second, Sentences sources,
+                              const Options &options = Options()) {
+    return enqueue(Job{first, second, std::move(sources), options, {}});
+  }
+
+ private:
+  struct Job {
+    Ptr<Model> first, second;
+    Sentences sources;
+    Options options;
+    std::promise<Response> promise;
+  };
+  std::future<Response> enqueue(Job job) {
+    std::future<Response> f = job.promise.get_future();
     {
       std::lock_guard<std::mutex> lock(mu_);
       queue_.push_back(std::move(job));
@@ -456,13 +547,7 @@ class Async {
     cv_.notify_one();
     return f;
   }
-
- private:
-  struct Job {
-    Sentences sources;
-    std::promise<Sentences> promise;
-  };
-  void work(const Ptr<Model> &model) {
+  void work() {
     Blocking service(config_);
     for (;;) {
       Job job;
@@ -474,14 +559,14 @@ class Async {
         queue_.pop_front();
       }
       try {
-        job.promise.set_value(service.translate(model, job.sources));
+        job.promise.set_value(job.second ? service.pivot(job.first, job.second, job.sources, job.options)
+                                         : service.translate(job.first, job.sources, job.options));
       } catch (...) {
         job.promise.set_exception(std::current_exception());
       }
     }
   }
   Config config_;
-  std::vector<Ptr<Model>> replicas_;
   std::vector<std::thread> workers_;
   std::deque<Job> queue_;
   std::mutex mu_;

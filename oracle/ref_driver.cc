@@ -10,7 +10,8 @@
 // Modes
 //   forward  --model M --batch B --out DIR [--dump] [--force F]
 //   qmm      --case C --out O
-//   bench    --model M --batches BS --workers N [--repeat R]
+//   bench    --model M --batches BS --workers N [--repeat R] [--tokens-out F]
+//            F (first repeat only): u32 n_batches, then per batch u32 B, then per sentence u32 len + u32 words[len]
 //   ops      --op layer_norm|softmax|highway|sdpa|sinusoid --in I --out O
 //
 // All files are raw little-endian; layouts are documented next to each reader.
@@ -287,7 +288,7 @@ int mode_qmm(int argc, char **argv) {
 // Workers pull batches from a shared atomic cursor like Async's worker loop
 // (reference slimt/Frontend.cc:207-227), all sharing one const Transformer.
 int mode_bench(int argc, char **argv) {
-  std::string model, batches;
+  std::string model, batches, tokens_out;
   int workers = 1, repeat = 1;
   for (int i = 2; i < argc; i++) {
     std::string a = argv[i];
@@ -295,6 +296,7 @@ int mode_bench(int argc, char **argv) {
     else if (a == "--batches") batches = argv[++i];
     else if (a == "--workers") workers = atoi(argv[++i]);
     else if (a == "--repeat") repeat = atoi(argv[++i]);
+    else if (a == "--tokens-out") tokens_out = argv[++i];
   }
   io::MmapFile mm(model);
   Transformer tf(6, 2, 8, 2, View{mm.data(), mm.size()});
@@ -304,6 +306,7 @@ int mode_bench(int argc, char **argv) {
   memcpy(&nb, p, 4), p += 4;
   std::vector<BatchSpec> specs(nb);
   for (auto &s : specs) p = read_batch(p, s);
+  std::vector<std::vector<Words>> kept(tokens_out.empty() ? 0 : specs.size());
 
   for (int rep = 0; rep < repeat; rep++) {
     std::atomic<size_t> cursor{0};
@@ -317,6 +320,7 @@ int mode_bench(int argc, char **argv) {
           if (i >= specs.size()) break;
           ForwardResult r = run_forward(tf, specs[i], "", nullptr);
           tokens += r.target_tokens;
+          if (rep == 0 && !kept.empty()) kept[i] = std::move(r.sentences);
           for (auto l : specs[i].lengths) src_tokens += l;
         }
       });
@@ -327,6 +331,18 @@ int mode_bench(int argc, char **argv) {
            "\"target_tokens_per_s\": %.3f}\n",
            rep, sec, size_t(tokens), size_t(src_tokens), workers, double(tokens) / sec);
     fflush(stdout);
+  }
+  if (!tokens_out.empty()) {
+    std::vector<uint32_t> flat;
+    flat.push_back(uint32_t(kept.size()));
+    for (const auto &batch : kept) {
+      flat.push_back(uint32_t(batch.size()));
+      for (const Words &w : batch) {
+        flat.push_back(uint32_t(w.size()));
+        flat.insert(flat.end(), w.begin(), w.end());
+      }
+    }
+    spit(tokens_out, flat.data(), 4 * flat.size());
   }
   return 0;
 }

@@ -25,12 +25,13 @@ EXPORTS = [
     "slimt_b200_qmm_affine", "slimt_b200_qmm_affine_debug", "slimt_b200_model_create", "slimt_b200_model_destroy",
     "slimt_b200_model_dims", "slimt_b200_model_forward", "slimt_b200_translate", "slimt_b200_kernel_launches",
     "slimt_b200_shortlist_generate", "slimt_b200_batcher_plan", "slimt_b200_profile_enable", "slimt_b200_profile_read",
+    "slimt_b200_translate_multi", "slimt_b200_shortlist_check",
 ]
 
 
 class ModelConfig(C.Structure):
     _fields_ = [("encoder_layers", C.c_int32), ("decoder_layers", C.c_int32), ("feed_forward_depth", C.c_int32),
-                ("num_heads", C.c_int32)]
+                ("num_heads", C.c_int32), ("eos_id", C.c_uint32), ("pad_id", C.c_uint32)]
 
 
 class ForwardIO(C.Structure):
@@ -44,8 +45,10 @@ class ForwardIO(C.Structure):
 class TranslateIO(C.Structure):
     _fields_ = [("tokens", C.c_void_p), ("offsets", C.c_void_p), ("n_sentences", C.c_size_t),
                 ("max_words", C.c_size_t), ("limit_factor", C.c_float), ("shortlist_bin", C.c_void_p),
-                ("shortlist_bytes", C.c_size_t), ("out_tokens", C.c_void_p), ("out_capacity", C.c_size_t),
-                ("out_offsets", C.c_void_p), ("target_tokens", C.c_uint64), ("batches", C.c_uint64),
+                ("shortlist_bytes", C.c_size_t), ("shortlist_check", C.c_int32), ("shortlist_shared", C.c_int32),
+                ("out_tokens", C.c_void_p), ("out_capacity", C.c_size_t), ("out_offsets", C.c_void_p),
+                ("out_alignments", C.c_void_p), ("align_capacity", C.c_size_t), ("out_align_offsets", C.c_void_p),
+                ("target_tokens", C.c_uint64), ("batches", C.c_uint64),
                 ("device_ms", C.c_double), ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64)]
 
@@ -89,6 +92,8 @@ def lib() -> C.CDLL:
         L.slimt_b200_model_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.slimt_b200_model_forward.argtypes = [C.c_void_p, C.POINTER(ForwardIO)]
         L.slimt_b200_translate.argtypes = [C.c_void_p, C.POINTER(TranslateIO)]
+        L.slimt_b200_translate_multi.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.POINTER(TranslateIO)]
+        L.slimt_b200_shortlist_check.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t]
         L.slimt_b200_shortlist_generate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
                                                     C.c_size_t, C.POINTER(C.c_size_t)]
         L.slimt_b200_batcher_plan.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -108,6 +113,12 @@ def shortlist_generate(shortlist_bin: bytes, words: np.ndarray, vocab: int) -> n
     _check(lib().slimt_b200_shortlist_generate(buf, len(shortlist_bin), _ptr(words), len(words), vocab, _ptr(out), len(out),
                                                C.byref(n)), "slimt_b200_shortlist_generate")
     return out[:n.value].copy()
+
+
+def shortlist_check(shortlist_bin: bytes, vocab: int) -> None:
+    """ShortlistGenerator::load with check = true (checksum + content_check); raises on a bad image."""
+    buf = (C.c_char * len(shortlist_bin)).from_buffer_copy(shortlist_bin)
+    _check(lib().slimt_b200_shortlist_check(buf, len(shortlist_bin), vocab), "slimt_b200_shortlist_check")
 
 
 def batcher_plan(lengths, max_words: int):
@@ -215,10 +226,10 @@ class Context:
 
 
 class Model:
-    def __init__(self, ctx: Context, model_bin: bytes, encoder_layers=6, decoder_layers=2, num_heads=8):
+    def __init__(self, ctx: Context, model_bin: bytes, encoder_layers=6, decoder_layers=2, num_heads=8, eos_id=0, pad_id=0):
         self.ctx = ctx
         self.h = C.c_void_p()
-        cfg = ModelConfig(encoder_layers, decoder_layers, 2, num_heads)
+        cfg = ModelConfig(encoder_layers, decoder_layers, 2, num_heads, eos_id, pad_id)
         buf = (C.c_char * len(model_bin)).from_buffer_copy(model_bin)
         _check(lib().slimt_b200_model_create(ctx.h, buf, len(model_bin), C.byref(cfg), C.byref(self.h)),
                "slimt_b200_model_create")
@@ -238,7 +249,7 @@ class Model:
         tokens = np.ascontiguousarray(tokens, dtype=np.uint32)
         lengths = np.ascontiguousarray(lengths, dtype=np.uint32)
         B, T = tokens.shape
-        max_steps = int(np.float32(limit_factor) * np.float32(T))
+        max_steps = max(1, int(np.float32(limit_factor) * np.float32(T)))
         sl = None if shortlist is None else np.ascontiguousarray(shortlist, dtype=np.uint32)
         nout = self.V if sl is None else len(sl)
         fo = None if forced is None else np.ascontiguousarray(forced, dtype=np.uint32)
@@ -263,34 +274,54 @@ class Model:
 
     def translate_flat(self, tokens: np.ndarray, offsets: np.ndarray, max_words: int, limit_factor: float = 1.5,
                        shortlist_bin: Optional[bytes] = None, out_tokens: Optional[np.ndarray] = None,
-                       out_offsets: Optional[np.ndarray] = None):
-        """slimt_b200_translate on caller-owned host buffers: ragged sentences in (tokens, offsets), ragged targets
-        out (out_tokens, out_offsets).  This is the C-ABI call a host integration makes; nothing is repacked."""
+                       out_offsets: Optional[np.ndarray] = None, replicas=None, want_alignments: bool = False,
+                       shortlist_check: bool = False, shortlist_shared: bool = False):
+        """slimt_b200_translate (or _translate_multi over `replicas`, a list of Models) on caller-owned host buffers:
+        ragged sentences in (tokens, offsets), ragged targets out (out_tokens, out_offsets).  This is the C-ABI call a
+        host integration makes; nothing is repacked."""
         n = len(offsets) - 1
+        lens = np.diff(offsets.astype(np.int64))
+        max_len = int(lens.max()) if n else 0
+        per = max(1, int(np.float32(limit_factor) * np.float32(max_len)))
         if out_offsets is None:
             out_offsets = np.zeros(n + 1, dtype=np.uint64)
         if out_tokens is None:
-            lens = np.diff(offsets.astype(np.int64))
-            max_len = int(lens.max()) if n else 0
-            out_tokens = np.zeros(max(1, n * (int(limit_factor * max_len) + 1)), dtype=np.uint32)
+            out_tokens = np.zeros(max(1, n * per), dtype=np.uint32)
+        align = align_offs = None
+        if want_alignments:
+            align = np.zeros(max(1, per * int(lens.sum())), dtype=np.float32)  # upper bound: every sentence decoded to the limit
+            align_offs = np.zeros(n + 1, dtype=np.uint64)
         slbuf = None
         if shortlist_bin is not None:
             slbuf = shortlist_bin if isinstance(shortlist_bin, C.Array) else (C.c_char * len(shortlist_bin)).from_buffer_copy(shortlist_bin)
         io = TranslateIO(_ptr(tokens), _ptr(offsets), n, max_words, limit_factor,
                          C.cast(slbuf, C.c_void_p) if slbuf is not None else None,
-                         0 if slbuf is None else len(slbuf), _ptr(out_tokens), len(out_tokens),
-                         _ptr(out_offsets), 0, 0, 0.0, 0, 0, 0)
-        _check(lib().slimt_b200_translate(self.h, C.byref(io)), "slimt_b200_translate")
+                         0 if slbuf is None else len(slbuf), int(shortlist_check), int(shortlist_shared),
+                         _ptr(out_tokens), len(out_tokens), _ptr(out_offsets),
+                         _ptr(align), 0 if align is None else len(align), _ptr(align_offs), 0, 0, 0.0, 0, 0, 0)
+        if replicas is None:
+            _check(lib().slimt_b200_translate(self.h, C.byref(io)), "slimt_b200_translate")
+        else:
+            hs = (C.c_void_p * len(replicas))(*[r.h for r in replicas])
+            _check(lib().slimt_b200_translate_multi(hs, len(replicas), C.byref(io)), "slimt_b200_translate_multi")
         stats = {"target_tokens": int(io.target_tokens), "batches": int(io.batches), "device_ms": io.device_ms,
                  "kernel_launches": int(io.kernel_launches), "h2d_bytes": int(io.h2d_bytes),
                  "d2h_bytes": int(io.d2h_bytes)}
+        if want_alignments:
+            stats["alignments"], stats["align_offsets"] = align, align_offs
         return out_tokens, out_offsets, stats
 
-    def translate(self, sentences, max_words: int, limit_factor: float = 1.5, shortlist_bin: Optional[bytes] = None):
+    def translate(self, sentences, max_words: int, limit_factor: float = 1.5, shortlist_bin: Optional[bytes] = None,
+                  replicas=None, want_alignments: bool = False, **kw):
         """exhaust() over one request: Batcher + shortlist + forward per batch, host buffers in and out."""
         offsets = np.zeros(len(sentences) + 1, dtype=np.uint64)
         offsets[1:] = np.cumsum([len(s) for s in sentences])
         tokens = np.concatenate([np.asarray(s, dtype=np.uint32) for s in sentences]) if sentences else np.zeros(0, np.uint32)
-        out_tokens, out_offsets, stats = self.translate_flat(tokens, offsets, max_words, limit_factor, shortlist_bin)
+        out_tokens, out_offsets, stats = self.translate_flat(tokens, offsets, max_words, limit_factor, shortlist_bin,
+                                                             replicas=replicas, want_alignments=want_alignments, **kw)
         outs = [out_tokens[int(out_offsets[i]):int(out_offsets[i + 1])].copy() for i in range(len(sentences))]
+        if want_alignments:
+            al, ao = stats.pop("alignments"), stats.pop("align_offsets")
+            stats["alignments"] = [al[int(ao[i]):int(ao[i + 1])].reshape(len(outs[i]), len(sentences[i])).copy()
+                                   for i in range(len(sentences))]
         return outs, stats

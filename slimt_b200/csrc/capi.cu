@@ -128,6 +128,7 @@ int slimt_b200_model_create(slimt_b200_ctx* ctx, const void* model_bin, size_t b
   }
   auto* m = new (std::nothrow) slimt_b200_model();
   if (!m) return 1;
+  m->m.eos_id = config->eos_id, m->m.pad_id = config->pad_id;
   if (m->m.load(&ctx->c, model_bin, bytes, config->encoder_layers, config->decoder_layers, config->num_heads)) {
     m->m.destroy();
     delete m;
@@ -162,143 +163,15 @@ int slimt_b200_model_forward(slimt_b200_model* model, slimt_b200_forward_io* io)
   return rc;
 }
 
-namespace {
-struct LazyShortlist {
-  const sb::ShortlistGenerator* gen;
-  const std::vector<uint32_t>* words;
-  size_t vocab;
-  std::vector<uint32_t> out;
-};
-int lazy_shortlist_cb(void* user, const uint32_t** words, size_t* n) {
-  auto* l = static_cast<LazyShortlist*>(user);
-  l->out = l->gen->generate(l->words->data(), l->words->size(), l->vocab);
-  *words = l->out.data();
-  *n = l->out.size();
-  return 0;
-}
-}  // namespace
-
 int slimt_b200_translate(slimt_b200_model* model, slimt_b200_translate_io* io) {
-  sb::Model& m = model->m;
-  sb::Context& c = *m.ctx;
-  const uint64_t l0 = c.launches, h0 = c.h2d_bytes, d0 = c.d2h_bytes;
-  sb::ShortlistGenerator gen;
-  const bool use_sl = io->shortlist_bin != nullptr && io->shortlist_bytes > 0;
-  if (use_sl && gen.load(io->shortlist_bin, io->shortlist_bytes)) return 1;
+  sb::Model* m = &model->m;
+  return sb::translate_multi(&m, 1, io);
+}
 
-  sb::Batcher batcher(io->max_words);
-  for (size_t i = 0; i < io->n_sentences; i++) batcher.enqueue(i, io->offsets[i + 1] - io->offsets[i]);
-
-  // record() (Model.cc:127-137) keeps each sentence's tokens up to and including its first EOS.  Each batch's kept
-  // tokens are packed into one block per batch (no per-sentence containers); the ragged output is written once every
-  // length is known.  The padded batch and the step-token matrix travel through one pinned staging block.
-  struct Done {
-    std::vector<size_t> ids;
-    std::vector<uint32_t> kept;  // the batch's sentences back to back, in batch row order
-  };
-  std::vector<Done> done;
-  std::vector<uint32_t> out_len(io->n_sentences, 0);
-  // staging layout: [padded tokens + lengths of the current batch][its step tokens]
-  size_t in_bytes = 0, steps_bytes = 0;
-  {
-    sb::Batcher plan(io->max_words);
-    for (size_t i = 0; i < io->n_sentences; i++) plan.enqueue(i, io->offsets[i + 1] - io->offsets[i]);
-    for (;;) {
-      size_t width = 0;
-      std::vector<size_t> b = plan.generate(&width);
-      if (b.empty()) break;
-      const size_t max_steps = static_cast<size_t>(io->limit_factor * static_cast<float>(width));
-      in_bytes = std::max(in_bytes, 4 * (b.size() * width + b.size()));
-      steps_bytes = std::max(steps_bytes, 4 * (std::max<size_t>(1, max_steps) + 1) * b.size());
-    }
-  }
-  in_bytes = (in_bytes + 255) & ~size_t(255);
-  char* stage = c.staging_reserve(in_bytes + steps_bytes + 256);
-  if (!stage) return 1;
-  io->target_tokens = 0, io->batches = 0, io->device_ms = 0;
-  cudaSetDevice(c.device);
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0), cudaEventCreate(&e1);
-  cudaEventRecord(e0, c.stream);
-  for (;;) {
-    size_t width = 0;
-    std::vector<size_t> batch = batcher.generate(&width);
-    if (batch.empty()) break;
-    // convert(): Batch -> padded Input (Frontend.cc:30-40; Input.cc:20-47), pad id 0
-    const size_t B = batch.size();
-    uint32_t* tokens = reinterpret_cast<uint32_t*>(stage);
-    uint32_t* lengths = tokens + B * width;
-    std::vector<uint32_t> words;
-    words.reserve(B * width);
-    for (size_t r = 0; r < B; r++) {
-      const size_t s = batch[r];
-      const size_t len = io->offsets[s + 1] - io->offsets[s];
-      memcpy(tokens + r * width, io->tokens + io->offsets[s], 4 * len);
-      memset(tokens + r * width + len, 0, 4 * (width - len));
-      lengths[r] = static_cast<uint32_t>(len);
-      words.insert(words.end(), io->tokens + io->offsets[s], io->tokens + io->offsets[s + 1]);
-    }
-    // Model::decode builds the candidate set before its first step (Model.cc:116-120); here the host does it
-    // while the GPU runs the encoder (the callback fires once the encoder kernels are queued)
-    LazyShortlist lazy{&gen, &words, static_cast<size_t>(m.V), {}};
-    const size_t max_steps = static_cast<size_t>(io->limit_factor * static_cast<float>(width));
-    // one row of up to max_steps tokens per sentence (transposed on the device) followed by the recorded lengths
-    const size_t stride = std::max<size_t>(1, max_steps);
-    uint32_t* rows = reinterpret_cast<uint32_t*>(stage + in_bytes);
-    uint32_t* lens = rows + stride * B;
-    sb::ForwardArgs a;
-    a.tokens = tokens, a.lengths = lengths, a.B = B, a.T = width;
-    a.limit_factor = io->limit_factor;
-    if (use_sl) a.shortlist_cb = lazy_shortlist_cb, a.shortlist_user = &lazy;
-    a.sentence_tokens = rows, a.row_stride = stride, a.target_lengths = lens;
-    if (sb::model_forward(m, a)) {
-      cudaEventDestroy(e0), cudaEventDestroy(e1);
-      return 1;
-    }
-    size_t kept_total = 0;
-    for (size_t r = 0; r < B; r++) {
-      out_len[batch[r]] = lens[r];
-      kept_total += lens[r];
-    }
-    std::vector<uint32_t> kept(kept_total);
-    size_t pos = 0;
-    for (size_t r = 0; r < B; r++) {
-      memcpy(kept.data() + pos, rows + r * stride, 4ul * lens[r]);
-      pos += lens[r];
-    }
-    done.push_back(Done{std::move(batch), std::move(kept)});
-    io->target_tokens += a.target_tokens;
-    io->batches += 1;
-  }
-  cudaEventRecord(e1, c.stream);
-  cudaEventSynchronize(e1);
-  float ms = 0;
-  cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0), cudaEventDestroy(e1);
-  io->device_ms = ms;
-
-  std::vector<uint64_t> out_off(io->n_sentences + 1, 0);
-  for (size_t i = 0; i < io->n_sentences; i++) out_off[i + 1] = out_off[i] + out_len[i];
-  const uint64_t off = out_off[io->n_sentences];
-  if (io->out_tokens && off > io->out_capacity) {
-    sb::set_error("out_tokens capacity too small");
-    return 1;
-  }
-  if (io->out_offsets) memcpy(io->out_offsets, out_off.data(), 8 * io->n_sentences);
-  if (io->out_tokens) {
-    for (const Done& d : done) {
-      size_t pos = 0;
-      for (size_t s : d.ids) {
-        memcpy(io->out_tokens + out_off[s], d.kept.data() + pos, 4ul * out_len[s]);
-        pos += out_len[s];
-      }
-    }
-  }
-  if (io->out_offsets) io->out_offsets[io->n_sentences] = off;
-  io->kernel_launches = c.launches - l0;
-  io->h2d_bytes = c.h2d_bytes - h0;
-  io->d2h_bytes = c.d2h_bytes - d0;
-  return 0;
+int slimt_b200_translate_multi(slimt_b200_model* const* replicas, size_t n_replicas, slimt_b200_translate_io* io) {
+  std::vector<sb::Model*> ms(n_replicas);
+  for (size_t i = 0; i < n_replicas; i++) ms[i] = replicas[i] ? &replicas[i]->m : nullptr;
+  return sb::translate_multi(ms.data(), n_replicas, io);
 }
 
 uint64_t slimt_b200_kernel_launches(const slimt_b200_ctx* ctx) { return ctx->c.launches; }
@@ -306,8 +179,9 @@ uint64_t slimt_b200_kernel_launches(const slimt_b200_ctx* ctx) { return ctx->c.l
 int slimt_b200_shortlist_generate(const void* shortlist_bin, size_t shortlist_bytes, const uint32_t* words,
                                   size_t n_words, size_t vocab, uint32_t* out, size_t out_capacity, size_t* n_out) {
   sb::ShortlistGenerator gen;
-  if (gen.load(shortlist_bin, shortlist_bytes)) return 1;
-  std::vector<uint32_t> r = gen.generate(words, n_words, vocab);
+  if (gen.load(shortlist_bin, shortlist_bytes, vocab, false)) return 1;
+  std::vector<uint32_t> r;
+  if (gen.generate(words, n_words, vocab, &r)) return 1;
   *n_out = r.size();
   if (r.size() > out_capacity) {
     sb::set_error("shortlist output capacity too small");
@@ -315,6 +189,11 @@ int slimt_b200_shortlist_generate(const void* shortlist_bin, size_t shortlist_by
   }
   memcpy(out, r.data(), 4 * r.size());
   return 0;
+}
+
+int slimt_b200_shortlist_check(const void* shortlist_bin, size_t shortlist_bytes, size_t vocab) {
+  sb::ShortlistGenerator gen;
+  return gen.load(shortlist_bin, shortlist_bytes, vocab, true);
 }
 
 int slimt_b200_batcher_plan(const uint64_t* lengths, size_t n, size_t max_words, uint64_t* batch_ids,

@@ -204,31 +204,58 @@ int parse_items(const void* bin, size_t bytes, std::map<std::string, Item>& out)
   struct Hdr {
     uint64_t name_len, type, shape_len, data_len;
   };
+  // every count below comes from the file: check it against what is left of the image before using it
+  auto left = [&p, end]() { return static_cast<uint64_t>(end - p); };
+  if (n > left() / sizeof(Hdr)) {
+    set_error("model image truncated: header table of " + std::to_string(n) + " items does not fit");
+    return 1;
+  }
   std::vector<Hdr> hdrs(n);
   for (auto& h : hdrs) {
     h.name_len = rd64(), h.type = rd64(), h.shape_len = rd64(), h.data_len = rd64();
   }
   std::vector<Item> items(n);
   for (uint64_t i = 0; i < n; i++) {
+    if (hdrs[i].name_len == 0 || hdrs[i].name_len > left()) {
+      set_error("model image truncated in the name table (item " + std::to_string(i) + ")");
+      return 1;
+    }
     items[i].name = std::string(p, hdrs[i].name_len - 1);
     items[i].type = hdrs[i].type;
     p += hdrs[i].name_len;
   }
   for (uint64_t i = 0; i < n; i++) {
+    if (hdrs[i].shape_len > 8 || 4 * hdrs[i].shape_len > left()) {
+      set_error("model image truncated or malformed in the shape table (item " + items[i].name + ")");
+      return 1;
+    }
     items[i].shape.resize(hdrs[i].shape_len);
     memcpy(items[i].shape.data(), p, 4 * hdrs[i].shape_len);
+    for (int d : items[i].shape)
+      if (d < 0) {
+        set_error("negative dimension in model item " + items[i].name);
+        return 1;
+      }
     p += 4 * hdrs[i].shape_len;
   }
+  if (left() < 8) {
+    set_error("model image truncated before the data section");
+    return 1;
+  }
   uint64_t pad = rd64();
+  if (pad > left()) {
+    set_error("model image truncated in the alignment padding");
+    return 1;
+  }
   p += pad;
   for (uint64_t i = 0; i < n; i++) {
-    items[i].data = p;
-    items[i].bytes = hdrs[i].data_len;
-    p += hdrs[i].data_len;
-    if (p > end) {
+    if (hdrs[i].data_len > left()) {
       set_error("model image truncated at item " + items[i].name);
       return 1;
     }
+    items[i].data = p;
+    items[i].bytes = hdrs[i].data_len;
+    p += hdrs[i].data_len;
     if (items[i].type != kTypeF32 && items[i].type != kTypeIG8 && items[i].type != 0x0101) {
       set_error("Incompatible type in model item " + items[i].name);
       return 1;
@@ -265,7 +292,7 @@ int Model::load(Context* c, const void* bin, size_t bytes, int enc_layers, int d
   auto f32_vec = [&](const std::string& name, size_t n, float** dst) -> int {
     const Item* it = need(name);
     if (!it) return 1;
-    if (it->elements() != n) {
+    if (it->elements() != n || it->bytes < n * 4) {
       set_error("parameter " + name + " has unexpected size");
       return 1;
     }
@@ -274,6 +301,10 @@ int Model::load(Context* c, const void* bin, size_t bytes, int enc_layers, int d
   auto scalar = [&](const std::string& name, float* v) -> int {
     const Item* it = need(name);
     if (!it) return 1;
+    if (it->bytes < 4) {
+      set_error("parameter " + name + " holds no value");
+      return 1;
+    }
     memcpy(v, it->data, 4);
     return 0;
   };
@@ -282,6 +313,10 @@ int Model::load(Context* c, const void* bin, size_t bytes, int enc_layers, int d
                     const std::string& aq_name = "") -> int {
     const Item* it = need(wname);
     if (!it) return 1;
+    if (it->shape.size() != 2 || it->bytes < static_cast<uint64_t>(it->shape[0]) * it->shape[1] + 4) {
+      set_error("weight " + wname + " is not a 2-D intgemm8 item followed by its quantization multiplier");
+      return 1;
+    }
     int K = it->shape[0], N = it->shape[1];
     const int8_t* q = reinterpret_cast<const int8_t*>(it->data);
     if (wname == "Wemb") std::swap(K, N);  // stored [V][E]: as an output weight K = E, N = V
@@ -294,7 +329,7 @@ int Model::load(Context* c, const void* bin, size_t bytes, int enc_layers, int d
     if (!bname.empty()) {
       const Item* b = need(bname);
       if (!b) return 1;
-      if (b->elements() != static_cast<size_t>(N)) {
+      if (b->elements() != static_cast<size_t>(N) || b->bytes < 4ull * N) {
         set_error("bias " + bname + " has unexpected size");
         return 1;
       }
@@ -327,6 +362,10 @@ int Model::load(Context* c, const void* bin, size_t bytes, int enc_layers, int d
 
   const Item* wemb = need("Wemb");
   if (!wemb) return 1;
+  if (wemb->shape.size() != 2 || wemb->bytes < static_cast<uint64_t>(wemb->shape[0]) * wemb->shape[1] + 4) {
+    set_error("Wemb is not a 2-D item followed by its quantization multiplier");
+    return 1;
+  }
   V = wemb->shape[0];
   E = wemb->shape[1];
   if (E % H != 0 || (E / H != 32 && E / H != 64)) {
@@ -405,6 +444,8 @@ int Model::load(Context* c, const void* bin, size_t bytes, int enc_layers, int d
 }
 
 void Model::destroy() {
+  for (auto& l : lanes) l->destroy();
+  lanes.clear();
   if (ctx) cudaSetDevice(ctx->device);
   for (void* p : owned) cudaFree(p);
   owned.clear();
@@ -491,6 +532,7 @@ void padd(GemmProblem* p, int8_t* ptr, float aq) {
 int qmm_affine_host(Context& c, const float* x, size_t M, size_t K, const int8_t* W, size_t N, const float* bias,
                     float aq, float bq, const uint32_t* indices, size_t n_idx, float* y, int8_t* qa_out,
                     int32_t* acc_out) {
+  std::lock_guard<std::recursive_mutex> ctx_lock(c.mu);
   SB_CUDA(cudaSetDevice(c.device));
   if (K % 64 != 0 || N % 8 != 0 || (indices && n_idx % 8 != 0)) {
     set_error("qmm::affine shape preconditions violated: K % 64 == 0, N % 8 == 0, indices % 8 == 0");
@@ -560,8 +602,14 @@ int qmm_affine_host(Context& c, const float* x, size_t M, size_t K, const int8_t
 }
 
 // ------------------------------------------------------------------ Model::forward
-int model_forward(Model& m, ForwardArgs& a) {
-  Context& c = *m.ctx;
+int model_forward(Model& m, ForwardArgs& a) { return model_forward_on(m, *m.ctx, a); }
+
+int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
+  std::lock_guard<std::recursive_mutex> ctx_lock(c.mu);
+  if (c.device != m.ctx->device) {
+    set_error("model_forward: the lane context and the model live on different devices");
+    return 1;
+  }
   SB_CUDA(cudaSetDevice(c.device));
   cudaStream_t s = c.stream;
   const int B = static_cast<int>(a.B), T = static_cast<int>(a.T), E = m.E, F = m.F, H = m.H, dh = m.dh;
@@ -578,12 +626,21 @@ int model_forward(Model& m, ForwardArgs& a) {
     set_error("decoder_layers must be 1 or 2");
     return 1;
   }
-  // Model.cc:160: size_t max_seq_length = limit_factor * source_sequence_length (float product, truncated)
-  const int max_steps = static_cast<int>(static_cast<size_t>(a.limit_factor * static_cast<float>(T)));
+  // Model.cc:160: size_t max_seq_length = limit_factor * source_sequence_length (float product, truncated).  The first
+  // decoder step runs before that loop (Model.cc:145-157), so at least one step is always executed and recorded.
+  const int max_steps = forward_max_steps(a.limit_factor, a.T);
   double src_tokens = static_cast<double>(R);  // cross-attention reads only valid keys; exact count when lengths are on the host
-  if (!a.device_io) {
+  if (!a.device_io || c.profiling) {
+    // per-kernel accounting only (profiling passes are never timed): with device-resident input the lengths are fetched
+    std::vector<uint32_t> lens_h(B);
+    const uint32_t* lp = a.lengths;
+    if (a.device_io) {
+      SB_CUDA(cudaMemcpyAsync(lens_h.data(), a.lengths, 4ul * B, cudaMemcpyDeviceToHost, s));
+      SB_CUDA(cudaStreamSynchronize(s));
+      lp = lens_h.data();
+    }
     src_tokens = 0;
-    for (int b = 0; b < B; b++) src_tokens += std::min<uint32_t>(a.lengths[b], T);
+    for (int b = 0; b < B; b++) src_tokens += std::min<uint32_t>(lp[b], T);
   }
   const bool lazy_sl = a.shortlist == nullptr && a.shortlist_cb != nullptr && !a.device_io;
   const bool use_sl = lazy_sl || (a.shortlist != nullptr && a.n_shortlist > 0);
@@ -606,12 +663,12 @@ int model_forward(Model& m, ForwardArgs& a) {
   for (int i = 0; i < 8; i++) acc(1ul * B * E);                 // decode int8 rows
   acc(1ul * B * F);
   acc(8ul * B), acc(B), acc(4ul * B), acc(256);                 // best, done, tgt_len, counters
-  acc(4ul * std::max(1, max_steps) * B);                        // step tokens
-  if (a.forced) acc(4ul * std::max(1, max_steps) * B);
-  if (a.sentence_tokens) acc(4ul * std::max(1, max_steps) * B);
+  acc(4ul * max_steps * B);                        // step tokens
+  if (a.forced) acc(4ul * max_steps * B);
+  if (a.sentence_tokens) acc(4ul * max_steps * B);
   if (use_sl) acc(4ul * Nout), acc(1ul * Nout * E), acc(4ul * Nout), acc(4ul * Nout), acc(4ul * (Nout / 32 + 1));
   if (a.logits) acc(4ul * B * Nout);
-  if (a.alignment) acc(4ul * B * T);
+  if (a.alignment) acc(4ul * max_steps * B * T);
   need += 64 * 256;
   if (c.reserve(need)) return 1;
 
@@ -712,7 +769,10 @@ int model_forward(Model& m, ForwardArgs& a) {
       QuantOuts q = qouts();
       qadd(q, attn_q, L.self.o.aq);
       LaunchScope ls(c, "enc_self_attention", 0, 13.0 * R * E);
-      launch_self_attention(Qb, Kb, Vb, d_lengths, B, T, H, dh, nullptr, q, s);
+      if (launch_self_attention(Qb, Kb, Vb, d_lengths, B, T, H, dh, nullptr, q, s)) {
+        set_error("self-attention: unsupported head size " + std::to_string(dh));
+        return 1;
+      }
     }
     }
     if (E == 256 && F == 1536) {
@@ -743,7 +803,8 @@ int model_forward(Model& m, ForwardArgs& a) {
       if (trace_buf && i == 0) k.trace = trace_buf + 2 * trace_n;
       const double Rd = R, Ed = E, Fd = F;
       LaunchScope ls(c, "enc_wo_ffn_fused", 2.0 * Rd * (Ed * Ed + 2.0 * Ed * Fd),
-                     Ed * Ed + 2.0 * Ed * Fd + Rd * Ed * (1.0 + 4.0 + 8.0 + 4.0 + k.n_zq));
+                     Ed * Ed + 2.0 * Ed * Fd + Rd * Ed * (1.0 + 4.0 + 4.0 + k.n_zq));  // u8 in, residual, f32 out, u8 copies
+      // (the y rows this variant parks in global memory and reads back are overhead, not algorithmic bytes)
       if (launch_rows_ffn(k, E, F, 128, s)) {
         set_error("fused encoder FFN kernel launch failed");
         return 1;
@@ -837,16 +898,16 @@ int model_forward(Model& m, ForwardArgs& a) {
   uint32_t* d_steps = nullptr;
   if (a.device_io) {
     d_steps = a.step_tokens;
-    c.take<uint32_t>(static_cast<size_t>(std::max(1, max_steps)) * B);
+    c.take<uint32_t>(static_cast<size_t>(max_steps) * B);
   } else {
-    d_steps = c.take<uint32_t>(static_cast<size_t>(std::max(1, max_steps)) * B);
+    d_steps = c.take<uint32_t>(static_cast<size_t>(max_steps) * B);
   }
   const uint32_t* d_forced = nullptr;
   if (a.forced) {
     if (a.device_io) {
       d_forced = a.forced;
     } else {
-      uint32_t* t = c.take<uint32_t>(static_cast<size_t>(std::max(1, max_steps)) * B);
+      uint32_t* t = c.take<uint32_t>(static_cast<size_t>(max_steps) * B);
       SB_CUDA(cudaMemcpyAsync(t, a.forced, 4ul * max_steps * B, cudaMemcpyHostToDevice, s));
       c.h2d_bytes += 4ul * max_steps * B;
       d_forced = t;
@@ -902,7 +963,8 @@ int model_forward(Model& m, ForwardArgs& a) {
   CUtensorMap map_oq, map_wout;
   if (c.make_map(&map_oq, oq, B, E, kBM) || c.make_map(&map_wout, Wout, Nout, E, 256)) return 1;
   float* d_logits = a.logits ? c.take<float>(static_cast<size_t>(B) * Nout) : nullptr;
-  float* d_align = a.alignment ? c.take<float>(static_cast<size_t>(B) * T) : nullptr;
+  // head-0 probabilities of every step stay on the device and come back in one copy after the loop
+  float* d_align_all = a.alignment ? c.take<float>(static_cast<size_t>(max_steps) * B * T) : nullptr;
 
   for (int l = 0; l < Ld; l++) SB_CUDA(cudaMemsetAsync(state[l], 0, 4ul * B * E, s));  // Decoder::start_states
   SB_CUDA(cudaMemsetAsync(best, 0, 8ul * B, s));
@@ -921,6 +983,7 @@ int model_forward(Model& m, ForwardArgs& a) {
   int executed = 0;
   int host_done = 0;
   for (int step = 0; step < max_steps; step++) {
+    float* d_align = d_align_all ? d_align_all + static_cast<size_t>(step) * B * T : nullptr;
     const float* in_f = xd;
     for (int l = 0; l < Ld; l++) {
       const DecLayerW& L = m.dec[l];
@@ -958,7 +1021,7 @@ int model_forward(Model& m, ForwardArgs& a) {
         k.attn_head0 = last ? d_align : nullptr;
         const double Bd = B, Ed = E;
         LaunchScope ls(c, "dec_cross_attention_rc", 2.0 * Bd * (T > 32 ? 64.0 : 32.0) * Ed * 2.0 * Ed,
-                       2.0 * Bd * T * Ed + 2.0 * Ed * Ed + 5.0 * Bd * Ed);
+                       2.0 * src_tokens * Ed + 2.0 * Ed * Ed + 5.0 * Bd * Ed);  // valid keys only
         if (launch_cross_attention_rc(k, c.num_sms, s)) {
           set_error("recompute cross-attention launch failed");
           return 1;
@@ -1025,17 +1088,12 @@ int model_forward(Model& m, ForwardArgs& a) {
         return 1;
       }
     }
-    if (d_align) {
-      SB_CUDA(cudaMemcpyAsync(a.alignment + static_cast<size_t>(step) * B * T, d_align, 4ul * B * T,
-                              cudaMemcpyDeviceToHost, s));
-      c.d2h_bytes += 4ul * B * T;
-    }
     {
       QuantOuts q = qouts();
       qadd(q, xq[0], m.dec[0].rnn_wf.aq), qadd(q, xq[1], m.dec[0].rnn_w.aq);
       LaunchScope ls(c, "dec_finalize_embed", 0, 7.0 * B * E + 20.0 * B);
-      launch_finalize_step(best, d_sl, d_forced, step, d_steps, done, tgt_len, counters, m.emb_q, m.inv_qm, m.sqrt_e,
-                           m.pos, B, E, xd, q, s);
+      launch_finalize_step(best, d_sl, d_forced, step, d_steps, done, tgt_len, counters, m.eos_id, m.emb_q, m.inv_qm,
+                           m.sqrt_e, m.pos, B, E, xd, q, s);
     }
     executed = step + 1;
     // Model.cc:161: the loop stops once every sentence has produced EOS.  The done-counter of each step is
@@ -1079,6 +1137,10 @@ int model_forward(Model& m, ForwardArgs& a) {
   // ---- results
   std::vector<uint32_t> lens(B);
   SB_CUDA(cudaMemcpyAsync(lens.data(), tgt_len, 4ul * B, cudaMemcpyDeviceToHost, s));
+  if (d_align_all && executed > 0) {
+    SB_CUDA(cudaMemcpyAsync(a.alignment, d_align_all, 4ul * executed * B * T, cudaMemcpyDeviceToHost, s));
+    c.d2h_bytes += 4ul * executed * B * T;
+  }
   if (!a.device_io && a.step_tokens && executed > 0) {
     SB_CUDA(cudaMemcpyAsync(a.step_tokens, d_steps, 4ul * executed * B, cudaMemcpyDeviceToHost, s));
     c.d2h_bytes += 4ul * executed * B;
@@ -1089,7 +1151,7 @@ int model_forward(Model& m, ForwardArgs& a) {
       return 1;
     }
     // one row per sentence: the host then copies each sentence's recorded prefix without striding through the matrix
-    uint32_t* d_rows = c.take<uint32_t>(static_cast<size_t>(std::max(1, max_steps)) * B);
+    uint32_t* d_rows = c.take<uint32_t>(static_cast<size_t>(max_steps) * B);
     {
       LaunchScope ls(c, "transpose_steps", 0, 8.0 * executed * B);
       launch_transpose_u32(d_steps, executed, B, d_rows, executed, s);

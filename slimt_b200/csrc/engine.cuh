@@ -7,6 +7,8 @@
 #include <stdint.h>
 
 #include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -30,6 +32,11 @@ const char* last_error();
   } while (0)
 
 struct Context {
+  // One stream, one workspace arena, one staging block and one set of polling slots per context: every entry point
+  // that touches them (qmm::*, Model::forward, the translate service) holds this lock for the duration of the call,
+  // so replicas or services that share a device context serialise instead of corrupting each other's workspace.
+  // Recursive because the service path calls model_forward with the lock held.
+  std::recursive_mutex mu;
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
@@ -147,7 +154,13 @@ struct Model {
   DevWeight out;            // Wemb_intgemm8 (re-quantised embedding) + decoder_ff_logit_out_b + none_QuantMultA
   float* pos = nullptr;     // sinusoidal table [max_pos][E]
   int max_pos = 0;
+  uint32_t eos_id = 0, pad_id = 0;  // Vocabulary::eos_id() / pad_id() (Vocabulary.hh:22-23); both 0 for browsermt vocabularies
   std::vector<void*> owned;
+  // extra lanes (stream + workspace + staging) on this model's device, created on demand by the service path
+  std::vector<std::unique_ptr<Context>> lanes;
+  std::mutex lanes_mu;
+  Context* lane(size_t i);  // lane 0 is the model's own context
+  int max_len() const { return max_pos < 256 ? max_pos : 256; }  // longest sentence a batch may hold
 
   int load(Context* c, const void* bin, size_t bytes, int enc_layers, int dec_layers, int heads);
   void destroy();
@@ -181,6 +194,16 @@ struct ForwardArgs {
 };
 
 int model_forward(Model& m, ForwardArgs& a);
+// The same pass with stream, workspace and staging taken from `lane` instead of the model's own context: weights are
+// read-only, so several lanes on the model's device can run batches of one model concurrently (translate.cu).
+int model_forward_on(Model& m, Context& lane, ForwardArgs& a);
+
+// Decoder steps Model::decode may run for a batch of width T: the first step is unconditional (Model.cc:145-157), the
+// loop that follows runs while i < size_t(limit_factor * T) (Model.cc:160-161).
+inline int forward_max_steps(float limit_factor, size_t T) {
+  const size_t n = static_cast<size_t>(limit_factor * static_cast<float>(T));
+  return static_cast<int>(n < 1 ? 1 : n);
+}
 
 // qmm::affine family on host buffers (operator-level drop-in + parity taps)
 int qmm_affine_host(Context& c, const float* x, size_t M, size_t K, const int8_t* W, size_t N, const float* bias,

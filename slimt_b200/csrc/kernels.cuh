@@ -27,7 +27,7 @@ void launch_quantize(const float* x, size_t n, QuantOuts q, cudaStream_t stream)
 
 // Encoder self-attention on unsplit [B*T][E] Q,K,V (scaled_dot_product_attention, slimt/Modules.cc:24-86,
 // with split_heads/join_heads folded into the addressing).  Emits the Wo operand (int8) and/or f32.
-void launch_self_attention(const float* Q, const float* K, const float* V, const uint32_t* lengths, int B, int T,
+int launch_self_attention(const float* Q, const float* K, const float* V, const uint32_t* lengths, int B, int T,
                            int H, int dh, float* out_f32, QuantOuts q, cudaStream_t stream);
 
 // Decoder cross-attention for one query row per sentence over cached K,V [B][S][E] (cross_attention.cu).
@@ -83,9 +83,9 @@ void launch_ssru_ln(const float* f, const float* wx, float* state, const float* 
 // step_tokens[step][B], EOS bookkeeping, re-arm `best`, and build the next step's decoder input
 // (embedding * sqrt(E) + position-0 signal; quirk Q1) with its int8 copies.
 void launch_finalize_step(unsigned long long* best, const uint32_t* shortlist, const uint32_t* forced, int step,
-                          uint32_t* step_tokens, uint8_t* done, uint32_t* tgt_len, int* n_done, const int8_t* emb_q, float inv_qm,
-                          float sqrt_e, const float* pos0, int B, int E, float* x, QuantOuts q,
-                          cudaStream_t stream);
+                          uint32_t* step_tokens, uint8_t* done, uint32_t* tgt_len, int* n_done, uint32_t eos_id,
+                          const int8_t* emb_q, float inv_qm, float sqrt_e, const float* pos0, int B, int E, float* x,
+                          QuantOuts q, cudaStream_t stream);
 
 // Shortlist: gather rows of the output weight and its prepared bias / shift terms.
 // c127 / c127_sel (127 * column sums, used by the fused output GEMM's bound filter) may be null.

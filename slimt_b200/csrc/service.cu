@@ -17,7 +17,15 @@ struct ShortlistHeader {
 };
 }  // namespace
 
-int ShortlistGenerator::load(const void* data, size_t bytes) {
+// std::hash<uint64_t> is the identity in libstdc++ (the library the reference is built with), so hash_combine
+// (slimt/Utils.hh:46-57) reduces to the boost formula on the raw words.
+static uint64_t hash_words(const uint64_t* data, size_t n) {
+  uint64_t seed = 0;
+  for (size_t i = 0; i < n; i++) seed ^= data[i] + 0x9e3779b9ull + (seed << 6) + (seed >> 2);
+  return seed;
+}
+
+int ShortlistGenerator::load(const void* data, size_t bytes, size_t vocab, bool check) {
   if (bytes < sizeof(ShortlistHeader)) {
     set_error("Shortlist length too short to have a header: " + std::to_string(bytes));
     return 1;
@@ -28,9 +36,12 @@ int ShortlistGenerator::load(const void* data, size_t bytes) {
     set_error("Incorrect magic in binary shortlist");
     return 1;
   }
-  const uint64_t expected = sizeof(h) + h.word_to_offset_size * 8 + h.shortlist_size * 4;
-  if (expected != bytes) {
-    set_error("Shortlist header claims file size should be " + std::to_string(expected) + " but file is " +
+  // header-implied size (Shortlist.cc:58-65); the counts come from the file, so the products must not wrap
+  const uint64_t room = bytes - sizeof(h);
+  if (h.word_to_offset_size > room / 8 || h.shortlist_size > (room - h.word_to_offset_size * 8) / 4 ||
+      sizeof(h) + h.word_to_offset_size * 8 + h.shortlist_size * 4 != bytes) {
+    set_error("Shortlist header claims file size should be " + std::to_string(sizeof(h)) + " + 8 * " +
+              std::to_string(h.word_to_offset_size) + " + 4 * " + std::to_string(h.shortlist_size) + " but file is " +
               std::to_string(bytes));
     return 1;
   }
@@ -39,22 +50,62 @@ int ShortlistGenerator::load(const void* data, size_t bytes) {
   const char* p = static_cast<const char*>(data) + sizeof(h);
   word_to_offset = reinterpret_cast<const uint64_t*>(p);
   shortlist = reinterpret_cast<const uint32_t*>(p + word_to_offset_size * 8);
+  if (check) {
+    // check = true of the reference's loader (Shortlist.cc:68-79, 30-37): checksum over everything after the
+    // header's first two words, then content_check()
+    const uint64_t* words = static_cast<const uint64_t*>(data) + 2;
+    if (hash_words(words, (bytes - 16) / 8) != h.checksum) {
+      set_error("checksum check failed: this binary shortlist is corrupted");
+      return 1;
+    }
+    if (word_to_offset_size == 0) {
+      set_error("Error: word_to_offset != shortlist_size");
+      return 1;
+    }
+    for (uint64_t i = 0; i + 1 < word_to_offset_size; i++)
+      if (word_to_offset[i] >= shortlist_size) {
+        set_error("Error: offset table not within shortlist size.");
+        return 1;
+      }
+    if (word_to_offset[word_to_offset_size - 1] != shortlist_size) {
+      set_error("Error: word_to_offset != shortlist_size");
+      return 1;
+    }
+    for (uint64_t j = 0; j < shortlist_size; j++)
+      if (shortlist[j] >= vocab) {
+        set_error("Error: shortlist indices are out of bounds");
+        return 1;
+      }
+  }
   return 0;
 }
 
-std::vector<uint32_t> ShortlistGenerator::generate(const uint32_t* words, size_t n, size_t vocab) const {
-  // byte tables instead of the reference's std::vector<bool>: same marks, no bit twiddling on the hot loop
+int ShortlistGenerator::generate(const uint32_t* words, size_t n, size_t vocab, std::vector<uint32_t>* out) const {
+  // byte tables instead of the reference's std::vector<bool>: same marks, no bit twiddling on the hot loop.  Unlike the
+  // reference with its default check = false, nothing read from the image is trusted: an offset or a target id
+  // outside its table is an error, not an out-of-bounds access.
   std::vector<uint8_t> source_table(word_to_offset_size, 0), target_table(vocab, 0);
   size_t ones = 0;
   for (uint32_t i = 0; i < frequent && i < vocab; ++i) target_table[i] = 1, ones++;
   // a large batch's union saturates the vocabulary early: once every id is marked nothing can change
   for (size_t t = 0; t < n && ones < vocab; t++) {
-    const uint32_t word = words[t];
+    const uint64_t word = words[t];
+    if (shared_vocabulary && word < vocab) {  // `shared_` (Shortlist.cc:132-134): a source word is its own candidate
+      ones += 1 - target_table[word];
+      target_table[word] = 1;
+    }
     if (word + 1 >= word_to_offset_size || source_table[word]) continue;
     source_table[word] = 1;
-    const uint32_t* p = shortlist + word_to_offset[word];
-    const uint32_t* e = shortlist + word_to_offset[word + 1];
-    for (; p != e; ++p) {
+    const uint64_t begin = word_to_offset[word], end = word_to_offset[word + 1];
+    if (begin > end || end > shortlist_size) {
+      set_error("Error: offset table not within shortlist size.");
+      return 1;
+    }
+    for (const uint32_t *p = shortlist + begin, *e = shortlist + end; p != e; ++p) {
+      if (*p >= vocab) {
+        set_error("Error: shortlist indices are out of bounds");
+        return 1;
+      }
       ones += 1 - target_table[*p];
       target_table[*p] = 1;
     }
@@ -66,11 +117,11 @@ std::vector<uint32_t> ShortlistGenerator::generate(const uint32_t* words, size_t
       ones++;
     }
   }
-  std::vector<uint32_t> indices(ones);
+  out->resize(ones);
   size_t k = 0;
   for (uint32_t i = 0; i < vocab; i++)
-    if (target_table[i]) indices[k++] = i;
-  return indices;
+    if (target_table[i]) (*out)[k++] = i;
+  return 0;
 }
 
 void Batcher::enqueue(size_t sentence, size_t length) {

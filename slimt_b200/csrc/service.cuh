@@ -20,9 +20,12 @@ struct ShortlistGenerator {
   uint64_t word_to_offset_size = 0;
   const uint32_t* shortlist = nullptr;
   uint64_t shortlist_size = 0;
-  int load(const void* data, size_t bytes);
+  bool shared_vocabulary = false;  // `shared_` of the reference (Shortlist.cc:132-134): source words are candidates too
+  // check = the reference loader's `check` argument (checksum + content_check, Shortlist.cc:30-37, 68-98); whatever
+  // its value, generate() never reads outside the image.  Nonzero return: see last_error().
+  int load(const void* data, size_t bytes, size_t vocab, bool check);
   // words: all source tokens of the batch; vocab: target vocabulary size.  Sorted ids, size % 8 == 0.
-  std::vector<uint32_t> generate(const uint32_t* words, size_t n, size_t vocab) const;
+  int generate(const uint32_t* words, size_t n, size_t vocab, std::vector<uint32_t>* out) const;
 };
 
 // Length-bucketed greedy batching over one request's sentences.
@@ -39,4 +42,10 @@ struct Batcher {
   size_t running_max_ = 0;
 };
 
+}  // namespace sb
+
+struct slimt_b200_translate_io;
+namespace sb {
+// exhaust() over one request with the batches dealt to the replicas' lanes (translate.cu)
+int translate_multi(Model* const* models, size_t n_replicas, slimt_b200_translate_io* io);
 }  // namespace sb

@@ -167,10 +167,23 @@ def make_shortlist(vocab: int = 32000, frequent: int = 100, best: int = 100, see
     return frequent, offsets, cand.reshape(-1)
 
 
-def write_shortlist(path: str, frequent: int, offsets: np.ndarray, lists: np.ndarray, best: int = 100) -> None:
-    header = struct.pack("<QQQQQQ", SHORTLIST_MAGIC, 0, frequent, best, len(offsets), len(lists))
+def shortlist_checksum(body: bytes) -> int:
+    """hash_bytes<uint64_t> (slimt/Utils.hh:46-68) over everything after the header's magic and checksum words:
+    boost-style hash_combine with std::hash<uint64_t>, which is the identity in libstdc++."""
+    seed, mask = 0, (1 << 64) - 1
+    for (w,) in struct.iter_unpack("<Q", body[:len(body) // 8 * 8]):
+        seed ^= (w + 0x9e3779b9 + ((seed << 6) & mask) + (seed >> 2)) & mask
+    return seed
+
+
+def write_shortlist(path: str, frequent: int, offsets: np.ndarray, lists: np.ndarray, best: int = 100,
+                    checksum: bool = False) -> None:
+    """`checksum`: compute the header's checksum (a Python loop over the image: small images only); otherwise it is
+    written as 0, which the reference's default check = false never looks at (Shortlist.hh:52)."""
+    body = struct.pack("<QQQQ", frequent, best, len(offsets), len(lists)) + offsets.astype("<u8").tobytes() + lists.astype("<u4").tobytes()
+    header = struct.pack("<QQ", SHORTLIST_MAGIC, shortlist_checksum(body) if checksum else 0)
     with open(path, "wb") as f:
-        f.write(header + offsets.astype("<u8").tobytes() + lists.astype("<u4").tobytes())
+        f.write(header + body)
 
 
 def make_sentences(n: int, length, vocab: int = 32000, seed: int = 99) -> List[np.ndarray]:

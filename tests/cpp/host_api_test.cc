@@ -84,19 +84,46 @@ int main(int argc, char **argv) {
     put(out, &n_align, 4);
     for (uint32_t s = 0; s < n_align; s++) put(out, histories[0]->alignment[s].data(), 4 * histories[0]->alignment[s].size());
 
-    // 3. Blocking::translate (Frontend.cc:91) with small batches
+    // 3. Blocking::translate (Frontend.cc:91) with small batches; once more with Options::alignment (Response.alignments)
     slimt::Config config;
     config.max_words = 96;
     slimt::Blocking blocking(config);
-    put_sentences(out, blocking.translate(model, sources));
+    slimt::Response plain = blocking.translate(model, sources);
+    put_sentences(out, plain.target);
+    slimt::Options with_alignment;
+    with_alignment.alignment = true;
+    slimt::Response aligned = blocking.translate(model, sources, with_alignment);
+    if (aligned.target != plain.target || aligned.alignments.size() != sources.size()) throw std::runtime_error("alignment run differs");
+    for (size_t i = 0; i < sources.size(); i++) {
+      uint32_t rows = aligned.alignments[i].size();
+      put(out, &rows, 4);
+      for (const auto &d : aligned.alignments[i]) {
+        if (d.size() != sources[i].size()) throw std::runtime_error("alignment row width");
+        put(out, d.data(), 4 * d.size());
+      }
+    }
 
-    // 4. Async::translate (Frontend.cc:229) through one replica
+    // 4. Async (Frontend.cc:207-323) with two workers over a model that holds TWO replicas on device 0: concurrent
+    // requests, each dealt batch by batch to both replicas; then Async::pivot (Frontend.cc:259-314)
     {
-      slimt::Async async(config, {model});
-      std::future<slimt::Sentences> f1 = async.translate(sources);
-      std::future<slimt::Sentences> f2 = async.translate(slimt::Sentences(sources.begin(), sources.begin() + 1));
-      put_sentences(out, f1.get());
-      put_sentences(out, f2.get());
+      auto two = std::make_shared<slimt::Model>(slimt::preset::tiny(), paths, std::vector<int>{0, 0});
+      config.workers = 2;
+      slimt::Async async(config);
+      std::future<slimt::Response> f1 = async.translate(two, sources);
+      std::future<slimt::Response> f2 = async.translate(two, slimt::Sentences(sources.begin(), sources.begin() + 1));
+      std::future<slimt::Response> f3 = async.pivot(two, model, sources, with_alignment);
+      std::future<slimt::Response> f4 = async.translate(model, sources);  // a second model on the same device, concurrently
+      put_sentences(out, f1.get().target);
+      put_sentences(out, f2.get().target);
+      slimt::Response pivoted = f3.get();
+      put_sentences(out, pivoted.target);
+      if (pivoted.alignments.size() != sources.size()) throw std::runtime_error("pivot alignments missing");
+      for (size_t i = 0; i < sources.size(); i++) {
+        if (pivoted.alignments[i].size() != pivoted.target[i].size()) throw std::runtime_error("pivot alignment rows");
+        for (const auto &d : pivoted.alignments[i])
+          if (d.size() != sources[i].size()) throw std::runtime_error("pivot alignment width");
+      }
+      if (f4.get().target != plain.target) throw std::runtime_error("concurrent request on a shared device context differs");
     }
     std::printf("host_api_test ok\n");
     return 0;

@@ -75,6 +75,39 @@ def test_shortlist_rejects_bad_images():
         capi.shortlist_generate(bytes(blob), np.zeros(1, np.uint32), 100)
 
 
+def test_shortlist_check_and_corrupt_contents():
+    """check = true of the reference's loader (Shortlist.cc:16-37, 68-98): checksum + content_check.  With or without
+    it, an image whose offsets or ids point outside their tables is reported, never followed."""
+    import struct
+    fr, offs, lists = synth.make_shortlist(vocab=100, frequent=5, best=3, seed=1, spread=10)
+    p = "/tmp/sl_chk.bin"
+    synth.write_shortlist(p, fr, offs, lists, best=3, checksum=True)
+    good = open(p, "rb").read()
+    capi.shortlist_check(good, 100)
+    words = np.array([1, 2, 3, 50], dtype=np.uint32)
+    assert len(capi.shortlist_generate(good, words, 100)) % 8 == 0
+    flipped = bytearray(good)
+    flipped[-1] ^= 0x01  # a target id changes: the checksum no longer matches
+    with pytest.raises(RuntimeError, match="checksum"):
+        capi.shortlist_check(bytes(flipped), 100)
+    with pytest.raises(RuntimeError, match="out of bounds"):
+        capi.shortlist_check(good, 50)  # image built for a larger vocabulary than the model's
+    with pytest.raises(RuntimeError, match="out of bounds"):
+        capi.shortlist_generate(good, words, 50)
+    # an offset beyond the list table
+    bad = bytearray(good)
+    struct.pack_into("<Q", bad, 48 + 8 * 3, 1 << 40)
+    with pytest.raises(RuntimeError, match="offset table"):
+        capi.shortlist_generate(bytes(bad), words, 100)
+    # a header whose counts would overflow the size arithmetic
+    huge = bytearray(good)
+    struct.pack_into("<QQ", huge, 32, (1 << 61) + 3, 1 << 62)
+    with pytest.raises(RuntimeError, match="file size"):
+        capi.shortlist_generate(bytes(huge), words, 100)
+    # source word id 0xFFFFFFFF must not wrap the `word + 1` bound
+    assert len(capi.shortlist_generate(good, np.array([0xFFFFFFFF, 3], dtype=np.uint32), 100)) % 8 == 0
+
+
 def test_prepare_weight_entry_points():
     lib = capi.lib()
     rng = np.random.RandomState(2)

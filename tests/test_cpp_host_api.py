@@ -91,14 +91,26 @@ def test_host_layer_matches_ctypes_path(gpu_ctx, tiny_model, shortlist_assets, t
         pos += 4 * int(lengths[0])
         assert np.array_equal(row, ref["attn"][s][0, 0, 0, :lengths[0]])
 
-    # 3. Blocking::translate == the ctypes translate with the same max_words; 4. Async twice
+    # 3. Blocking::translate == the ctypes translate with the same max_words (tokens and Response.alignments)
     m = capi.Model(gpu_ctx, open(path, "rb").read())
-    outs, _ = m.translate(sents, max_words=96, shortlist_bin=open(sl_path, "rb").read())
+    sl_bin = open(sl_path, "rb").read()
+    outs, st = m.translate(sents, max_words=96, shortlist_bin=sl_bin, want_alignments=True)
     blocking, pos = _read_sentences(buf, pos)
     assert blocking == [o.tolist() for o in outs]
+    for i, s in enumerate(sents):
+        rows, = struct.unpack_from("<I", buf, pos)
+        pos += 4
+        assert rows == len(outs[i])
+        a = np.frombuffer(buf, dtype=np.float32, count=rows * len(s), offset=pos).reshape(rows, len(s))
+        pos += 4 * rows * len(s)
+        assert np.array_equal(a, st["alignments"][i])
+    # 4. Async over two replicas on one device, twice; Async::pivot == translate(translate(.))
     a1, pos = _read_sentences(buf, pos)
     a2, pos = _read_sentences(buf, pos)
+    a3, pos = _read_sentences(buf, pos)
     assert a1 == blocking
-    one, _ = m.translate(sents[:1], max_words=96, shortlist_bin=open(sl_path, "rb").read())
+    one, _ = m.translate(sents[:1], max_words=96, shortlist_bin=sl_bin)
     assert a2 == [one[0].tolist()]
+    second, _ = m.translate(outs, max_words=96, shortlist_bin=sl_bin)
+    assert a3 == [o.tolist() for o in second]
     m.close()
