@@ -233,17 +233,14 @@ inline cudaError_t ensure_dyn_smem(Kern kern, size_t bytes) {
   int dev = 0;
   cudaGetDevice(&dev);
   const unsigned long long key = (static_cast<unsigned long long>(dev) << 56) ^ reinterpret_cast<unsigned long long>(kern);
-  {
-    std::lock_guard<std::mutex> g(mu);
-    auto it = done.find(key);
-    if (it != done.end() && it->second >= bytes) return cudaSuccess;
-  }
+  // The attribute is set under the lock and only ever raised: two lanes of one device may ask for different sizes of
+  // the same kernel at the same time, and a smaller request landing after a larger one would shrink the limit under
+  // the other lane's next launch.
+  std::lock_guard<std::mutex> g(mu);
+  size_t& v = done[key];
+  if (v >= bytes) return cudaSuccess;
   const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
-  if (e == cudaSuccess) {
-    std::lock_guard<std::mutex> g(mu);
-    size_t& v = done[key];
-    if (bytes > v) v = bytes;
-  }
+  if (e == cudaSuccess) v = bytes;
   return e;
 }
 
