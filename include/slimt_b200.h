@@ -29,6 +29,13 @@ const char* slimt_b200_version(void);
 int slimt_b200_ctx_create(int device, slimt_b200_ctx** out);
 void slimt_b200_ctx_destroy(slimt_b200_ctx* ctx);
 int slimt_b200_ctx_synchronize(slimt_b200_ctx* ctx);
+/* Arithmetic mode of everything launched through the context.  0 (default): bit-exact restatement of the reference's
+ * float arithmetic (results identical to slimt's CPU path with exact int32 accumulation).  1: tolerance mode
+ * (FMA-contracted dequantisation, tree-reduced LayerNorm sums, ex2/rcp softmax and sigmoid, integer argmax proxy),
+ * held to logits rtol 1e-3 and >= 99 % greedy token agreement instead of bit equality.  The environment variable
+ * SLIMT_B200_MATH=fast sets the default of new contexts. */
+int slimt_b200_ctx_set_math(slimt_b200_ctx* ctx, int fast);
+int slimt_b200_ctx_get_math(const slimt_b200_ctx* ctx);
 
 /* Device buffers and device-side timing on the context's stream, for callers
  * (bench, tests) that keep inputs resident in HBM. */

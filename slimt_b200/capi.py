@@ -25,7 +25,7 @@ EXPORTS = [
     "slimt_b200_qmm_affine", "slimt_b200_qmm_affine_debug", "slimt_b200_model_create", "slimt_b200_model_destroy",
     "slimt_b200_model_dims", "slimt_b200_model_forward", "slimt_b200_translate", "slimt_b200_kernel_launches",
     "slimt_b200_shortlist_generate", "slimt_b200_batcher_plan", "slimt_b200_profile_enable", "slimt_b200_profile_read",
-    "slimt_b200_translate_multi", "slimt_b200_shortlist_check",
+    "slimt_b200_translate_multi", "slimt_b200_shortlist_check", "slimt_b200_ctx_set_math", "slimt_b200_ctx_get_math",
 ]
 
 
@@ -75,6 +75,8 @@ def lib() -> C.CDLL:
         L.slimt_b200_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         L.slimt_b200_ctx_destroy.argtypes = [C.c_void_p]
         L.slimt_b200_ctx_synchronize.argtypes = [C.c_void_p]
+        L.slimt_b200_ctx_set_math.argtypes = [C.c_void_p, C.c_int]
+        L.slimt_b200_ctx_get_math.argtypes = [C.c_void_p]
         L.slimt_b200_timer_start.argtypes = [C.c_void_p]
         L.slimt_b200_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.slimt_b200_flush_l2.argtypes = [C.c_void_p, C.c_size_t]
@@ -159,6 +161,13 @@ class Context:
 
     def synchronize(self):
         _check(lib().slimt_b200_ctx_synchronize(self.h), "synchronize")
+
+    def set_math(self, fast: bool):
+        """False: bit-exact mode (default).  True: tolerance mode (logits rtol 1e-3, >= 99 % tokens)."""
+        _check(lib().slimt_b200_ctx_set_math(self.h, int(fast)), "set_math")
+
+    def math(self) -> str:
+        return "fast" if lib().slimt_b200_ctx_get_math(self.h) else "exact"
 
     def launches(self) -> int:
         return int(lib().slimt_b200_kernel_launches(self.h))

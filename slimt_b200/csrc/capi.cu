@@ -44,6 +44,13 @@ int slimt_b200_ctx_synchronize(slimt_b200_ctx* ctx) {
   return 0;
 }
 
+int slimt_b200_ctx_set_math(slimt_b200_ctx* ctx, int fast) {
+  std::lock_guard<std::recursive_mutex> g(ctx->c.mu);
+  ctx->c.fast = fast != 0;
+  return 0;
+}
+int slimt_b200_ctx_get_math(const slimt_b200_ctx* ctx) { return ctx->c.fast ? 1 : 0; }
+
 void* slimt_b200_dev_alloc(slimt_b200_ctx* ctx, size_t bytes) {
   cudaSetDevice(ctx->c.device);
   void* p = nullptr;

@@ -47,7 +47,8 @@ struct Smem {
   static constexpr int ps = qs + kGroup * kE * 4;     // f32 [4][8][32]
   static constexpr int pbk = ps + kGroup * kH * kKeys * 4;  // f32 [256]
   static constexpr int pmax = pbk + kE * 4;           // f32 [4 key blocks][8 heads]: per-block score maxima (KB > 1)
-  static constexpr int exp_tab = pmax + kGroup * kH * 4;  // u64 [32]
+  static constexpr int psum = pmax + kGroup * kH * 4;     // f32 [4 key blocks][8 heads]: per-block sums (tolerance mode, KB > 1)
+  static constexpr int exp_tab = psum + kGroup * kH * 4;  // u64 [32]
   static constexpr int bars = exp_tab + 32 * 8;
   // w_full ak_full av_full ak_free av_free k_done v_done k_drained v_drained
   static constexpr int n_bars = 9;
@@ -55,7 +56,12 @@ struct Smem {
   static constexpr int total = tmem_slot + 16 + 1024;
 };
 
-template <int KB>  // 32-key blocks per sentence (1: S <= 32, 2: S <= 64)
+// kFast (tolerance mode): the dequantisation is folded out of the inner loops.  K = um_k * acc_k + pb_k, so
+// q . K[key] = um_k * sum_d q[d] * acc_k[key][d] + q . pb_k, and the second term is the same for every key of a (sentence,
+// head): it cancels in the softmax and is never formed.  V = um_v * acc_v + pb_v and the probabilities sum to one, so
+// sum_key p[key] * V[key][f] = um_v * sum_key p[key] * acc_v[f][key] + pb_v[f].  Per element that leaves one int -> float
+// conversion and one FMA; the softmax uses ex2 / rcp and shuffle-tree sums.
+template <int KB, bool kFast>  // 32-key blocks per sentence (1: S <= 32, 2: S <= 64)
 __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const __grid_constant__ CrossRcArgs a) {
   constexpr int NS = kGroup / KB;  // sentences per group
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -68,6 +74,7 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
   float* s_p = reinterpret_cast<float*>(smem + Smem::ps);
   float* s_pbk = reinterpret_cast<float*>(smem + Smem::pbk);
   float* s_pmax = reinterpret_cast<float*>(smem + Smem::pmax);
+  float* s_psum = reinterpret_cast<float*>(smem + Smem::psum);
   uint64_t* exp_tab = reinterpret_cast<uint64_t*>(smem + Smem::exp_tab);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
   uint64_t* w_full = bars;
@@ -254,6 +261,70 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(k_drained);
+        constexpr int kRow = KB * kKeys;  // probabilities of one (sentence, head)
+        float* prow = s_p + (j * kH + h0) * kRow;
+        if constexpr (kFast) {
+          // scores in the log2 domain, up to a per-(sentence, head) constant (see the kernel comment)
+          float sc[2];
+          {
+            const float* qh = s_q + j * kE + h0 * kDH;
+            float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+            for (int d = 0; d < kDH; d += 4) {
+              const float4 q0 = *reinterpret_cast<const float4*>(qh + d);
+              const float4 q1 = *reinterpret_cast<const float4*>(qh + kDH + d);
+              acc0 = fmaf(q0.x, __int2float_rn(static_cast<int>(v0[d])), acc0);
+              acc1 = fmaf(q1.x, __int2float_rn(static_cast<int>(v1[d])), acc1);
+              acc0 = fmaf(q0.y, __int2float_rn(static_cast<int>(v0[d + 1])), acc0);
+              acc1 = fmaf(q1.y, __int2float_rn(static_cast<int>(v1[d + 1])), acc1);
+              acc0 = fmaf(q0.z, __int2float_rn(static_cast<int>(v0[d + 2])), acc0);
+              acc1 = fmaf(q1.z, __int2float_rn(static_cast<int>(v1[d + 2])), acc1);
+              acc0 = fmaf(q0.w, __int2float_rn(static_cast<int>(v0[d + 3])), acc0);
+              acc1 = fmaf(q1.w, __int2float_rn(static_cast<int>(v1[d + 3])), acc1);
+            }
+            const float sk = a.dk * a.um_k * 1.4426950408889634f;
+            sc[0] = valid ? acc0 * sk : -3.402823466e+38f;
+            sc[1] = valid ? acc1 * sk : -3.402823466e+38f;
+          }
+          float mx[2] = {sc[0], sc[1]};
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], o));
+          }
+          if constexpr (KB > 1) {
+            if (lane < 2) s_pmax[qd * kH + h0 + lane] = mx[lane];
+            named_bar_sync(2 + kj * 4 + sub, KB * 32);
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+              for (int o = 0; o < KB; o++) mx[hh] = fmaxf(mx[hh], s_pmax[(kj * KB + o) * kH + h0 + hh]);
+          }
+          float e[2], sum[2];
+#pragma unroll
+          for (int hh = 0; hh < 2; hh++) {
+            e[hh] = valid ? exp2_fast(sc[hh] - mx[hh]) : 0.0f;
+            sum[hh] = warp_sum(e[hh]);
+          }
+          if constexpr (KB > 1) {
+            if (lane < 2) s_psum[qd * kH + h0 + lane] = sum[lane];
+            named_bar_sync(2 + kj * 4 + sub, KB * 32);
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+              float t = 0.0f;
+#pragma unroll
+              for (int o = 0; o < KB; o++) t += s_psum[(kj * KB + o) * kH + h0 + hh];
+              sum[hh] = t;
+            }
+          }
+#pragma unroll
+          for (int hh = 0; hh < 2; hh++) {
+            const float p = e[hh] * rcp_fast(sum[hh]);
+            prow[hh * kRow + key] = p;
+            if (a.attn_head0 != nullptr && h0 + hh == 0 && b < a.B && key < a.T)
+              a.attn_head0[static_cast<size_t>(b) * a.T + key] = p;
+          }
+        } else {
         // the two heads' fma chains advance together (source order is what the in-order issue sees)
         float sc[2];
         {
@@ -281,8 +352,6 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
         // softmax over the sentence's keys (slimt/TensorOps.cc:282-315): max, exp, sum in key order, divide.  Both
         // heads advance together: nothing is stored between the two expf evaluations (a store would pin the second
         // one's table load behind it), so their double-precision chains interleave.
-        constexpr int kRow = KB * kKeys;  // probabilities of one (sentence, head)
-        float* prow = s_p + (j * kH + h0) * kRow;
         float mx[2], e[2], sum[2];
 #pragma unroll
         for (int hh = 0; hh < 2; hh++) mx[hh] = valid ? sc[hh] : -3.402823466e+38f;
@@ -331,6 +400,7 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
           if (a.attn_head0 != nullptr && h0 + hh == 0 && b < a.B && key < a.T)
             a.attn_head0[static_cast<size_t>(b) * a.T + key] = p;
         }
+        }  // exact K phase
       }
       named_bar_sync(1, kConsThreads);
 
@@ -349,9 +419,51 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
         auto emit = [&](int b, float acc) {
           const size_t off = static_cast<size_t>(b) * kE + v_feat;
           if (a.out_f32) a.out_f32[off] = acc;
-          for (int k = 0; k < a.qo.n; k++) a.qo.ptr[k][off] = static_cast<int8_t>(quantize1(acc, a.qo.aq[k]));
+          for (int k = 0; k < a.qo.n; k++) a.qo.ptr[k][off] = static_cast<int8_t>(quantize<kFast>(acc, a.qo.aq[k]));
         };
         constexpr int kRow = KB * kKeys;
+        if constexpr (kFast) {
+          // probabilities of keys past a sentence's length are exactly 0, so every chain runs over the whole block
+          if constexpr (KB == 1) {
+            const int j0 = vj0;
+            const float* pr0 = s_p + (j0 * kH + v_head) * kKeys;
+            const float* pr1 = pr0 + kH * kKeys;
+            float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+            for (int l = 0; l < kKeys; l += 4) {
+              const float4 p0 = *reinterpret_cast<const float4*>(pr0 + l);
+              const float4 p1 = *reinterpret_cast<const float4*>(pr1 + l);
+              acc0 = fmaf(p0.x, __int2float_rn(static_cast<int>(v0[l])), acc0);
+              acc1 = fmaf(p1.x, __int2float_rn(static_cast<int>(v1[l])), acc1);
+              acc0 = fmaf(p0.y, __int2float_rn(static_cast<int>(v0[l + 1])), acc0);
+              acc1 = fmaf(p1.y, __int2float_rn(static_cast<int>(v1[l + 1])), acc1);
+              acc0 = fmaf(p0.z, __int2float_rn(static_cast<int>(v0[l + 2])), acc0);
+              acc1 = fmaf(p1.z, __int2float_rn(static_cast<int>(v1[l + 2])), acc1);
+              acc0 = fmaf(p0.w, __int2float_rn(static_cast<int>(v0[l + 3])), acc0);
+              acc1 = fmaf(p1.w, __int2float_rn(static_cast<int>(v1[l + 3])), acc1);
+            }
+            if (b0 + j0 < a.B) emit(b0 + j0, fmaf(a.um_v, acc0, pbv));
+            if (b0 + j0 + 1 < a.B) emit(b0 + j0 + 1, fmaf(a.um_v, acc1, pbv));
+          } else {
+            const int j = vj0;
+            const float* pr = s_p + (j * kH + v_head) * kRow;
+            float acc0 = 0.0f, acc1 = 0.0f;  // the two key blocks advance together
+#pragma unroll
+            for (int l = 0; l < kKeys; l += 4) {
+              const float4 p0 = *reinterpret_cast<const float4*>(pr + l);
+              const float4 p1 = *reinterpret_cast<const float4*>(pr + kKeys + l);
+              acc0 = fmaf(p0.x, __int2float_rn(static_cast<int>(v0[l])), acc0);
+              acc1 = fmaf(p1.x, __int2float_rn(static_cast<int>(v1[l])), acc1);
+              acc0 = fmaf(p0.y, __int2float_rn(static_cast<int>(v0[l + 1])), acc0);
+              acc1 = fmaf(p1.y, __int2float_rn(static_cast<int>(v1[l + 1])), acc1);
+              acc0 = fmaf(p0.z, __int2float_rn(static_cast<int>(v0[l + 2])), acc0);
+              acc1 = fmaf(p1.z, __int2float_rn(static_cast<int>(v1[l + 2])), acc1);
+              acc0 = fmaf(p0.w, __int2float_rn(static_cast<int>(v0[l + 3])), acc0);
+              acc1 = fmaf(p1.w, __int2float_rn(static_cast<int>(v1[l + 3])), acc1);
+            }
+            if (b0 + j < a.B) emit(b0 + j, fmaf(a.um_v, acc0 + acc1, pbv));
+          }
+        } else
         if constexpr (KB == 1) {
           const int j0 = vj0;
           if (len_v[0] == kKeys && len_v[1] == kKeys && b0 + j0 + 1 < a.B) {
@@ -445,12 +557,13 @@ bool cross_attention_rc_supported(int E, int H, int dh, int S) {
   return E == kE && H == kH && dh == kDH && S >= 1 && S <= 2 * kKeys;
 }
 
-int launch_cross_attention_rc(const CrossRcArgs& a, int num_sms, cudaStream_t stream) {
+int launch_cross_attention_rc(const CrossRcArgs& a, int num_sms, bool fast, cudaStream_t stream) {
   if (a.B == 0) return 0;
   const bool two = a.T > kKeys;  // sentences of 33..64 tokens take two key blocks each
   const int per_group = two ? kGroup / 2 : kGroup;
   const int groups = (a.B + per_group - 1) / per_group;
-  auto kern = two ? cross_attention_rc_kernel<2> : cross_attention_rc_kernel<1>;
+  auto kern = two ? (fast ? cross_attention_rc_kernel<2, true> : cross_attention_rc_kernel<2, false>)
+                  : (fast ? cross_attention_rc_kernel<1, true> : cross_attention_rc_kernel<1, false>);
   if (ensure_dyn_smem(kern, Smem::total) != cudaSuccess) return 1;
   return launch_pdl(kern, dim3(groups < num_sms ? groups : num_sms), dim3(kThreadsRc), Smem::total, stream, a) != cudaSuccess;
 }

@@ -76,6 +76,7 @@ int Context::init(int dev) {
     return 1;
   }
   encode_tiled = reinterpret_cast<decltype(encode_tiled)>(fn);
+  if (const char* e = getenv("SLIMT_B200_MATH")) fast = strcmp(e, "fast") == 0;
   SB_CUDA(cudaMallocHost(&done_slots, 8 * sizeof(int)));
   for (auto& e : done_events) SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return 0;
@@ -402,6 +403,9 @@ int Model::load(Context* c, const void* bin, size_t bytes, int enc_layers, int d
     SB_CUDA(cudaMalloc(&out.dmax, 4ul * ((V + 31) / 32)));
     owned.push_back(out.dmax);
     launch_out_bounds(out.c127, out.pb, out.um, V, out.dmax, c->stream);
+    SB_CUDA(cudaMalloc(&out.ipb6, 4ul * ((V + 255) / 256 * 256)));
+    owned.push_back(out.ipb6);
+    launch_out_ipb(out.c127, out.pb, out.um, V, out.ipb6, c->stream);
     SB_CUDA(cudaStreamSynchronize(c->stream));
     std::vector<float> pbh(V);
     SB_CUDA(cudaMemcpy(pbh.data(), out.pb, 4ul * V, cudaMemcpyDeviceToHost));
@@ -666,7 +670,7 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
   acc(4ul * max_steps * B);                        // step tokens
   if (a.forced) acc(4ul * max_steps * B);
   if (a.sentence_tokens) acc(4ul * max_steps * B);
-  if (use_sl) acc(4ul * Nout), acc(1ul * Nout * E), acc(4ul * Nout), acc(4ul * Nout), acc(4ul * (Nout / 32 + 1));
+  if (use_sl) acc(4ul * Nout), acc(1ul * Nout * E), acc(4ul * Nout), acc(4ul * Nout), acc(4ul * (Nout / 32 + 1)), acc(4ul * (Nout + 256));
   if (a.logits) acc(4ul * B * Nout);
   if (a.alignment) acc(4ul * max_steps * B * T);
   need += 64 * 256;
@@ -805,7 +809,7 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
       LaunchScope ls(c, "enc_wo_ffn_fused", 2.0 * Rd * (Ed * Ed + 2.0 * Ed * Fd),
                      Ed * Ed + 2.0 * Ed * Fd + Rd * Ed * (1.0 + 4.0 + 4.0 + k.n_zq));  // u8 in, residual, f32 out, u8 copies
       // (the y rows this variant parks in global memory and reads back are overhead, not algorithmic bytes)
-      if (launch_rows_ffn(k, E, F, 128, s)) {
+      if (launch_rows_ffn(k, E, F, 128, c.fast, s)) {
         set_error("fused encoder FFN kernel launch failed");
         return 1;
       }
@@ -930,6 +934,7 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
   const float* pb_out = m.out.pb;
   const int32_t* c127_out = m.out.c127;
   const float* dmax_out = m.out.dmax;
+  const int32_t* ipb6_out = m.out.ipb6;
   if (use_sl) {
     if (a.device_io) {
       d_sl = a.shortlist;
@@ -953,7 +958,12 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
       LaunchScope ls(c, "out_bounds", 0, 8.0 * Nout);
       launch_out_bounds(cs, pbs, m.out.um, Nout, dms, s);
     }
-    Wout = Ws, pb_out = pbs, c127_out = cs, dmax_out = dms;
+    int32_t* ips = c.take<int32_t>(static_cast<size_t>(Nout) + 256);
+    if (c.fast) {
+      LaunchScope ls(c, "out_bounds", 0, 12.0 * Nout);
+      launch_out_ipb(cs, pbs, m.out.um, Nout, ips, s);
+    }
+    Wout = Ws, pb_out = pbs, c127_out = cs, dmax_out = dms, ipb6_out = ips;
   }
   CUtensorMap map_xq[2], map_zq[2], map_caq;  // u8 activation operands of the row-tile kernels, box {128 B, 32 rows}
   for (int i = 0; i < 2; i++) {
@@ -1002,7 +1012,7 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
         if (trace_buf && step == 3 && l == 0) k.trace = trace_buf;
         const double Bd = B, Ed = E;
         LaunchScope ls(c, "dec_ssru_q_fused", 2.0 * Bd * 3.0 * Ed * Ed, 3.0 * Ed * Ed + Bd * Ed * (2.0 + 4.0 * 5.0));
-        if (launch_dec_ssru(k, E, s)) {
+        if (launch_dec_ssru(k, E, c.fast, s)) {
           set_error("fused SSRU kernel: unsupported embedding size " + std::to_string(E));
           return 1;
         }
@@ -1022,7 +1032,7 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
         const double Bd = B, Ed = E;
         LaunchScope ls(c, "dec_cross_attention_rc", 2.0 * Bd * (T > 32 ? 64.0 : 32.0) * Ed * 2.0 * Ed,
                        2.0 * src_tokens * Ed + 2.0 * Ed * Ed + 5.0 * Bd * Ed);  // valid keys only
-        if (launch_cross_attention_rc(k, c.num_sms, s)) {
+        if (launch_cross_attention_rc(k, c.num_sms, c.fast, s)) {
           set_error("recompute cross-attention launch failed");
           return 1;
         }
@@ -1058,7 +1068,7 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
         const double Bd = B, Ed = E, Fd = F;
         LaunchScope ls(c, "dec_wo_ffn_fused", 2.0 * Bd * (Ed * Ed + 2.0 * Ed * Fd),
                        Ed * Ed + 2.0 * Ed * Fd + Bd * Ed * (1.0 + 4.0 + (last ? 1.0 : 6.0)));
-        if (launch_rows_ffn(k, E, F, kRowTile, s)) {
+        if (launch_rows_ffn(k, E, F, kRowTile, c.fast, s)) {
           set_error("fused FFN kernel: unsupported sizes E=" + std::to_string(E) + " F=" + std::to_string(F));
           return 1;
         }
@@ -1082,8 +1092,8 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
     } else {
       const double Md = B, Nd = Nout, Kd = E;
       LaunchScope ls(c, "dec_gemm_out_argmax", 2.0 * Md * Nd * Kd, Md * Kd + Nd * Kd + 4.0 * Nd + 8.0 * Md);
-      if (launch_gemm_out_argmax(map_oq, map_wout, pb_out, c127_out, dmax_out, m.out.um, m.out.eta, B, Nout, E, best,
-                                 c.num_sms, s)) {
+      if (launch_gemm_out_argmax(map_oq, map_wout, pb_out, c127_out, dmax_out, c.fast ? ipb6_out : nullptr, m.out.um,
+                                 m.out.eta, B, Nout, E, best, c.num_sms, s)) {
         set_error("output GEMM: unsupported K " + std::to_string(E));
         return 1;
       }

@@ -37,6 +37,11 @@ struct Context {
   // so replicas or services that share a device context serialise instead of corrupting each other's workspace.
   // Recursive because the service path calls model_forward with the lock held.
   std::recursive_mutex mu;
+  // Arithmetic mode of every kernel launched through this context.  false (default): bit-exact restatement of the
+  // reference's float arithmetic (the verifier).  true (SLIMT_B200_MATH=fast or slimt_b200_ctx_set_math): tolerance
+  // mode -- FMA-contracted dequantisation, tree-reduced LayerNorm statistics, ex2/rcp-based softmax and sigmoid,
+  // integer argmax proxy -- held to north_star's bars (logits rtol 1e-3, >= 99 % greedy tokens) instead of bit equality.
+  bool fast = false;
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
@@ -118,6 +123,7 @@ struct DevWeight {
   int32_t* c127 = nullptr;  // [N] 127 * colsum
   float* dmax = nullptr;    // [ceil(N/32)]
   float eta = 0;            // slack covering the float roundings of the exact epilogue
+  int32_t* ipb6 = nullptr;  // [ceil(N/256)*256] integer logit-proxy offsets (tolerance mode, gemm_out.cu)
 };
 
 struct DevLN {

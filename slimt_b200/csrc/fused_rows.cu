@@ -34,7 +34,7 @@ struct SsruSmem {
   static constexpr int total = tmem_slot + 16 + 1024;
 };
 
-template <int E>
+template <int E, bool kFast>
 __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_constant__ DecSsruArgs a) {
   using L = SsruSmem<E>;
   constexpr int EK = E / 128, EM = E / 128;
@@ -181,9 +181,15 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
 #pragma unroll
           for (int r = 0; r < 8; r++) {
             const int grow = row0 + rq * 8 + r;
-            const float sg = sigmoid_ref_tab(dequant1(static_cast<int>(vf[r]), a.um_f, pbf), exp_tab);
-            const float wx = dequant1(static_cast<int>(vw[r]), a.um_w, pbw);
-            const float c = __fadd_rn(__fmul_rn(sg, st[mb][r]), __fmul_rn(__fsub_rn(1.0f, sg), wx));
+            float sg, c;
+            const float wx = dequant<kFast>(static_cast<int>(vw[r]), a.um_w, pbw);
+            if constexpr (kFast) {
+              sg = sigmoid_fast(dequant<true>(static_cast<int>(vf[r]), a.um_f, pbf));
+              c = fmaf(sg, st[mb][r] - wx, wx);  // sg * c_prev + (1 - sg) * Wx
+            } else {
+              sg = sigmoid_ref_tab(dequant1(static_cast<int>(vf[r]), a.um_f, pbf), exp_tab);
+              c = __fadd_rn(__fmul_rn(sg, st[mb][r]), __fmul_rn(__fsub_rn(1.0f, sg), wx));
+            }
             if (grow < a.M) a.state[static_cast<size_t>(grow) * E + f] = c;
             xs[(rq * 8 + r) * XS + f] = __fadd_rn(xv[mb][r], c > 0.0f ? c : 0.0f);
           }
@@ -191,15 +197,16 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
       }
       named_bar_sync(1, kEpiThreads);
       if (et == 0) SB_TRACE(a, 5);
-      if (et < kR) ln_stats_row<E>(xs + et * XS, &stats[et], &stats[32 + et], a.eps);
+      if constexpr (kFast) ln_stats_fast<E, kR>(xs, stats, a.eps, ew, lane);
+      else if (et < kR) ln_stats_row<E>(xs + et * XS, &stats[et], &stats[32 + et], a.eps);
       named_bar_sync(1, kEpiThreads);
       if (et == 0) SB_TRACE(a, 6);
       {
         const float g = a.ln_scale[nf], b = a.ln_bias[nf];
 #pragma unroll 4
         for (int r = nr0; r < nr0 + kRowsPer; r++) {
-          const float y = ln_apply(xs[r * XS + nf], stats[r], stats[32 + r], g, b);
-          opnd_h[opnd_off<kR>(r, nf)] = quant_byte(y, a.aq_q, false);
+          const float y = ln_apply_t<kFast>(xs[r * XS + nf], stats[r], stats[32 + r], g, b);
+          opnd_h[opnd_off<kR>(r, nf)] = static_cast<uint8_t>(quantize<kFast>(y, a.aq_q));
           const int grow = row0 + r;
           if (grow < a.M) a.h_out[static_cast<size_t>(grow) * E + nf] = y;
         }
@@ -223,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
 #pragma unroll
         for (int r = 0; r < 8; r++) {
           const int grow = row0 + rq * 8 + r;
-          if (grow < a.M) a.q_out[static_cast<size_t>(grow) * E + f] = dequant1(static_cast<int>(v[r]), a.um_q, pb);
+          if (grow < a.M) a.q_out[static_cast<size_t>(grow) * E + f] = dequant<kFast>(static_cast<int>(v[r]), a.um_q, pb);
         }
       }
       if (et == 0) SB_TRACE(a, 11);
@@ -251,9 +258,13 @@ int launch_rows(Kern kern, const Args& a, size_t smem, cudaStream_t stream) {
 
 }  // namespace
 
-int launch_dec_ssru(const DecSsruArgs& a, int E, cudaStream_t stream) {
-  if (E == 256) return launch_rows(dec_ssru_kernel<256>, a, SsruSmem<256>::total, stream);
-  if (E == 512) return launch_rows(dec_ssru_kernel<512>, a, SsruSmem<512>::total, stream);
+int launch_dec_ssru(const DecSsruArgs& a, int E, bool fast, cudaStream_t stream) {
+  if (E == 256)
+    return fast ? launch_rows(dec_ssru_kernel<256, true>, a, SsruSmem<256>::total, stream)
+                : launch_rows(dec_ssru_kernel<256, false>, a, SsruSmem<256>::total, stream);
+  if (E == 512)
+    return fast ? launch_rows(dec_ssru_kernel<512, true>, a, SsruSmem<512>::total, stream)
+                : launch_rows(dec_ssru_kernel<512, false>, a, SsruSmem<512>::total, stream);
   return 1;
 }
 

@@ -67,7 +67,7 @@ struct DecSsruArgs {
 
 // E = 256, F = 1536 (tiny) and E = 512, F = 2048 (base) are built.  Returns nonzero when unsupported.
 // rows_per_tile: 32 (decoder step) or 128 (encoder; E = 256 only).
-int launch_rows_ffn(const RowsFfnArgs& a, int E, int F, int rows_per_tile, cudaStream_t stream);
-int launch_dec_ssru(const DecSsruArgs& a, int E, cudaStream_t stream);
+int launch_rows_ffn(const RowsFfnArgs& a, int E, int F, int rows_per_tile, bool fast, cudaStream_t stream);
+int launch_dec_ssru(const DecSsruArgs& a, int E, bool fast, cudaStream_t stream);
 
 }  // namespace sb

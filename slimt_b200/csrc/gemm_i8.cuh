@@ -70,8 +70,10 @@ void launch_gemm_i8(const GemmBatch& batch, int n_problems, int epilogue, int BN
 // {128 B, 128 rows}; tma_b: s8 [N][K] with box {128 B, 256 rows}; c127 [N] = 127 * colsum(B); dmax
 // [ceil(N/32)] and eta from launch_out_bounds; best [M] packed (ordered value << 32 | ~index), pre-zeroed.
 // Returns nonzero for an unsupported K (128 * {2, 4} are built).
+// ipb6 != nullptr selects the tolerance-mode epilogue (integer proxy argmax, see gemm_out.cu): ipb6 [ceil(N/256)*256]
+// from launch_out_ipb; pb / c127 / dmax / eta are then unused.
 int launch_gemm_out_argmax(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const float* pb, const int32_t* c127,
-                           const float* dmax, float um, float eta, int M, int N, int K, unsigned long long* best,
-                           int num_sms, cudaStream_t stream);
+                           const float* dmax, const int32_t* ipb6, float um, float eta, int M, int N, int K,
+                           unsigned long long* best, int num_sms, cudaStream_t stream);
 
 }  // namespace sb

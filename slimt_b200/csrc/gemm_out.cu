@@ -19,6 +19,7 @@
 // roundings of the exact formula.  Only when ub can reach the row's best so far (read back from `best`,
 // which other CTAs keep raising) are the 32 exact logits evaluated; a skipped chunk cannot contain the
 // maximum, so the result is still the reference's first strict maximum.
+#include <limits.h>
 #include <stdio.h>
 
 #include "exact_math.cuh"
@@ -40,11 +41,18 @@ __device__ __forceinline__ unsigned long long pack_best_out(float v, uint32_t id
   return (static_cast<unsigned long long>(key) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - idx);
 }
 
-template <int KB>  // K = 128 * KB bytes per row
+// kFast (SLIMT_B200_MATH=fast): the greedy choice is taken on an INTEGER proxy of the logit instead of the float logit.
+// y = um * (v' + c127[n]) + pb[n] = um * (v' + t[n]) with t[n] = c127[n] + pb[n] / um, and um > 0, so the argmax of y
+// is the argmax of v' + t[n]; t[n] is rounded to an integer once per batch (ipb), which moves a logit by at most half
+// a quantum um (~1e-5 of the logit range).  The epilogue is then two integer instructions per element -- x = (v' << 6)
+// + ipb6[n] with ipb6[n] = (ipb[n] << 6) + (63 - n % 64) carrying the column's position inside the thread's 64-column
+// strip so that ties keep the lowest index, and a running max -- with no divergence and no exact path.
+template <int KB, bool kFast>  // K = 128 * KB bytes per row
 __global__ void __launch_bounds__(kOutThreads, 1)
     out_argmax_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                       const float* __restrict__ pb, const int32_t* __restrict__ c127, const float* __restrict__ dmax,
-                      float um, float eta, int M, int N, unsigned long long* __restrict__ best) {
+                      const int32_t* __restrict__ ipb6, float um, float eta, int M, int N,
+                      unsigned long long* __restrict__ best) {
   constexpr int kABytes = kBM * kBK;        // one k-block of A
   constexpr int kBBytes = kOutBN * kBK;     // one k-block of B
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -170,6 +178,60 @@ __global__ void __launch_bounds__(kOutThreads, 1)
     const int q = warp & 3;
     const int quarter = e >> 2;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + quarter * 64;
+    if constexpr (kFast) {
+      uint32_t i = 0;
+      unsigned long long seen_next = 0ull;
+      if (t_begin < t_end) {
+        const int row = (t_begin % m_tiles) * kBM + q * 32 + lane;
+        seen_next = row < M ? __ldcg(best + row) : ~0ull;
+      }
+      for (int t = t_begin; t < t_end; t++, i++) {
+        const int n = t / m_tiles, m = t % m_tiles;
+        const uint32_t buf = i & 1;
+        const unsigned long long seen = seen_next;
+        if (t + 1 < t_end) {
+          const int row = ((t + 1) % m_tiles) * kBM + q * 32 + lane;
+          seen_next = row < M ? __ldcg(best + row) : ~0ull;
+        }
+        const int nb0 = n * kOutBN + quarter * 64;
+        const int row = m * kBM + q * 32 + lane;
+        // the strip's 64 proxy offsets: the same addresses for every lane and every row tile of this column run (L1)
+        const int4* ip = reinterpret_cast<const int4*>(ipb6 + nb0);
+        mbar_wait(&tmem_full[buf], (i >> 1) & 1);
+        tc_fence_after();
+        uint32_t v0[32], v1[32];
+        tmem_ld32_nowait(lane_addr + buf * kOutBN, v0);
+        tmem_ld32_nowait(lane_addr + buf * kOutBN + 32, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[buf]);  // accumulators are in registers: release the buffer
+        int x0 = INT_MIN, x1 = INT_MIN, x2 = INT_MIN, x3 = INT_MIN;  // four independent max chains
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int4 c = __ldg(ip + (j >> 2));
+          x0 = max(x0, (static_cast<int>(v0[j]) << 6) + c.x);
+          x1 = max(x1, (static_cast<int>(v0[j + 1]) << 6) + c.y);
+          x2 = max(x2, (static_cast<int>(v0[j + 2]) << 6) + c.z);
+          x3 = max(x3, (static_cast<int>(v0[j + 3]) << 6) + c.w);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int4 c = __ldg(ip + 8 + (j >> 2));
+          x0 = max(x0, (static_cast<int>(v1[j]) << 6) + c.x);
+          x1 = max(x1, (static_cast<int>(v1[j + 1]) << 6) + c.y);
+          x2 = max(x2, (static_cast<int>(v1[j + 2]) << 6) + c.z);
+          x3 = max(x3, (static_cast<int>(v1[j + 3]) << 6) + c.w);
+        }
+        const int x = max(max(x0, x1), max(x2, x3));
+        if (row < M) {
+          const uint32_t col = static_cast<uint32_t>(nb0 + 63 - (x & 63));
+          const uint32_t key = static_cast<uint32_t>(x >> 6) ^ 0x80000000u;  // order-preserving int -> uint
+          const unsigned long long packed = (static_cast<unsigned long long>(key) << 32) | (0xFFFFFFFFu - col);
+          if (packed > seen) atomicMax(best + row, packed);
+        }
+      }
+    } else {
     const float ninf = -__int_as_float(0x7f800000);
     const int nch = (N + 31) >> 5;
     // prefetched per-tile inputs of the bound filter
@@ -276,6 +338,7 @@ __global__ void __launch_bounds__(kOutThreads, 1)
         if (key > seen) atomicMax(best + row, key);
       }
     }
+    }  // exact epilogue
   }
 
   tc_fence_before();
@@ -288,29 +351,22 @@ size_t out_smem_bytes(int KB) { return static_cast<size_t>(KB) * kOutBN * kBK + 
 }  // namespace
 
 int launch_gemm_out_argmax(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const float* pb, const int32_t* c127,
-                           const float* dmax, float um, float eta, int M, int N, int K, unsigned long long* best,
-                           int num_sms, cudaStream_t stream) {
+                           const float* dmax, const int32_t* ipb6, float um, float eta, int M, int N, int K,
+                           unsigned long long* best, int num_sms, cudaStream_t stream) {
   const int KB = K / kBK;
   const long tiles = static_cast<long>((M + kBM - 1) / kBM) * ((N + kOutBN - 1) / kOutBN);
   const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
   if (grid == 0) return 0;
   const size_t smem = out_smem_bytes(KB);
-  if (KB == 2) {
-    auto kern = out_argmax_kernel<2>;
-    ensure_dyn_smem(kern, smem);
-    if (launch_pdl(kern, dim3(grid), dim3(kOutThreads), smem, stream, tma_a, tma_b, pb, c127, dmax, um, eta, M, N, best) !=
-        cudaSuccess)
-      return 1;
-  } else if (KB == 4) {
-    auto kern = out_argmax_kernel<4>;
-    ensure_dyn_smem(kern, smem);
-    if (launch_pdl(kern, dim3(grid), dim3(kOutThreads), smem, stream, tma_a, tma_b, pb, c127, dmax, um, eta, M, N, best) !=
-        cudaSuccess)
-      return 1;
-  } else {
-    return 1;
-  }
-  return 0;
+  const bool fast = ipb6 != nullptr;
+  auto go = [&](auto kern) {
+    if (ensure_dyn_smem(kern, smem) != cudaSuccess) return 1;
+    return launch_pdl(kern, dim3(grid), dim3(kOutThreads), smem, stream, tma_a, tma_b, pb, c127, dmax, ipb6, um, eta, M, N,
+                      best) != cudaSuccess ? 1 : 0;
+  };
+  if (KB == 2) return fast ? go(out_argmax_kernel<2, true>) : go(out_argmax_kernel<2, false>);
+  if (KB == 4) return fast ? go(out_argmax_kernel<4, true>) : go(out_argmax_kernel<4, false>);
+  return 1;
 }
 
 }  // namespace sb

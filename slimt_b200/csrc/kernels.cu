@@ -2,6 +2,7 @@
 // round-to-nearest intrinsics in the reference's evaluation order.
 #include "kernels.cuh"
 
+#include <limits.h>
 #include <stdio.h>
 
 #include "exact_math.cuh"
@@ -278,6 +279,22 @@ __global__ void out_bounds_kernel(const int32_t* __restrict__ c127, const float*
   if (lane == 0) dmax[chunk] = __double2float_ru(d);
 }
 
+// ipb6[n] = (round(c127[n] + pb[n] / um) << 6) + (63 - n % 64): the per-column offset of the tolerance-mode output
+// GEMM's integer logit proxy (gemm_out.cu), evaluated in double.  Entries from N up to the end of the last 256-column
+// tile get the most negative value that cannot overflow when a zero accumulator is added.
+__global__ void out_ipb_kernel(const int32_t* __restrict__ c127, const float* __restrict__ pb, float um, int N, int n_pad,
+                               int32_t* __restrict__ ipb6) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_pad) return;
+  if (n >= N) {
+    ipb6[n] = INT_MIN + 64;
+    return;
+  }
+  double t = rint(static_cast<double>(c127[n]) + static_cast<double>(pb[n]) / static_cast<double>(um));
+  t = fmin(fmax(t, -16777216.0), 16777216.0);  // |accumulator| < 2^22, so (v' + ipb) << 6 stays inside int32
+  ipb6[n] = (static_cast<int32_t>(t) << 6) + (63 - (n & 63));
+}
+
 __device__ __forceinline__ unsigned long long pack_best_k(float v, uint32_t idx) {
   if (v == 0.0f) v = 0.0f;
   uint32_t bits = __float_as_uint(v);
@@ -364,6 +381,12 @@ void launch_out_bounds(const int32_t* c127, const float* pb, float um, int N, fl
   const int chunks = (N + 31) / 32;
   if (chunks == 0) return;
   out_bounds_kernel<<<(chunks + 7) / 8, 256, 0, stream>>>(c127, pb, um, N, dmax);
+}
+
+void launch_out_ipb(const int32_t* c127, const float* pb, float um, int N, int32_t* ipb6, cudaStream_t stream) {
+  const int n_pad = (N + 255) / 256 * 256;
+  if (n_pad == 0) return;
+  out_ipb_kernel<<<(n_pad + 255) / 256, 256, 0, stream>>>(c127, pb, um, N, n_pad, ipb6);
 }
 
 __global__ void transpose_u32_kernel(const uint32_t* __restrict__ src, int rows, int cols, uint32_t* __restrict__ dst,

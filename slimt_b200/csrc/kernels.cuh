@@ -55,7 +55,7 @@ struct CrossRcArgs {
   float* attn_head0;           // optional [B][T]
 };
 bool cross_attention_rc_supported(int E, int H, int dh, int S);
-int launch_cross_attention_rc(const CrossRcArgs& a, int num_sms, cudaStream_t stream);
+int launch_cross_attention_rc(const CrossRcArgs& a, int num_sms, bool fast, cudaStream_t stream);
 
 // Encoder self-attention fused with its q/k/v projections (enc_attention.cu): Q, K and V never reach HBM.
 // Bit-identical to launch_gemm_i8(EPI_F32) x 3 followed by launch_self_attention.
@@ -94,6 +94,9 @@ void launch_gather_rows(const int8_t* W, const float* pb, const int32_t* c127, c
 
 // dmax[ceil(N/32)]: per 32-column chunk, max_n(c127[n] * um + pb[n]) rounded up (see gemm_out.cu).
 void launch_out_bounds(const int32_t* c127, const float* pb, float um, int N, float* dmax, cudaStream_t stream);
+
+// ipb6[ceil(N/256)*256]: integer logit-proxy offsets of the tolerance-mode output GEMM (see gemm_out.cu).
+void launch_out_ipb(const int32_t* c127, const float* pb, float um, int N, int32_t* ipb6, cudaStream_t stream);
 
 // Row-wise first-max over f32 logits (used when logits are materialised for parity taps).
 void launch_argmax_rows(const float* logits, int rows, int cols, unsigned long long* best, cudaStream_t stream);

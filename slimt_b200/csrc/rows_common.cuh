@@ -88,6 +88,40 @@ __device__ __forceinline__ float ln_apply(float x, float mean, float sigma, floa
   return __fadd_rn(__fmul_rn(g, __fdiv_rn(__fsub_rn(x, mean), sigma)), b);
 }
 
+// LayerNorm statistics of R rows parked in xs (row stride E + 1 floats), all kEpiWarps warps cooperating: a warp owns
+// rows ew, ew + 16, ...; its lanes stride over the features and meet in a shuffle tree.  stats[row] = mean,
+// stats[R + row] = 1 / sqrt(var + eps) (the exact path stores sigma there and divides).
+template <int E, int R>
+__device__ __forceinline__ void ln_stats_fast(const float* xs, float* stats, float eps, int ew, int lane) {
+  constexpr int kPer = E / 32;
+  for (int row = ew; row < R; row += kEpiWarps) {
+    const float* xr = xs + row * (E + 1);
+    float v[kPer];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kPer; i++) {
+      v[i] = xr[lane + 32 * i];
+      s += v[i];
+    }
+    const float mean = warp_sum(s) * (1.0f / static_cast<float>(E));
+    float sq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kPer; i++) {
+      const float d = v[i] - mean;
+      sq = fmaf(d, d, sq);
+    }
+    sq = warp_sum(sq);
+    if (lane == 0) {
+      stats[row] = mean;
+      stats[R + row] = rsqrtf(fmaf(sq, 1.0f / static_cast<float>(E), eps));
+    }
+  }
+}
+template <bool kFast>
+__device__ __forceinline__ float ln_apply_t(float x, float mean, float sigma_or_rstd, float g, float b) {
+  if constexpr (kFast) return fmaf((x - mean) * sigma_or_rstd, g, b);
+  else return ln_apply(x, mean, sigma_or_rstd, g, b);
+}
 // Streams one weight tile per call through the ring (producer side).
 struct RingProducer {
   uint8_t* ring;

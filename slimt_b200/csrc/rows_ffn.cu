@@ -51,7 +51,7 @@ struct FfnPlan {
   static_assert(total <= 227 * 1024, "shared memory");
 };
 
-template <int E, int F, int R>
+template <int E, int F, int R, bool kFast>
 __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_constant__ RowsFfnArgs a) {
   using L = FfnPlan<E, F, R>;
   constexpr int EK = L::EK, EM = L::EM, FM = L::FM, XS = L::XS, kOpK = L::kOpK;
@@ -251,11 +251,12 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
         tmem_ld_wait();
 #pragma unroll
         for (int r = 0; r < RPW; r++)
-          xs[(cg * RPW + r) * XS + f] = __fadd_rn(dequant1(static_cast<int>(v[r]), a.um_o, pb), res[r]);
+          xs[(cg * RPW + r) * XS + f] = __fadd_rn(dequant<kFast>(static_cast<int>(v[r]), a.um_o, pb), res[r]);
       }
       named_bar_sync(1, kEpiThreads);
       if (et == 0) SB_TRACE(a, 5);
-      if (et < R) ln_stats_row<E>(xs + et * XS, &stats[et], &stats[R + et], a.eps);
+      if constexpr (kFast) ln_stats_fast<E, R>(xs, stats, a.eps, ew, lane);
+      else if (et < R) ln_stats_row<E>(xs + et * XS, &stats[et], &stats[R + et], a.eps);
       named_bar_sync(1, kEpiThreads);
       if (et == 0) SB_TRACE(a, 6);
       // y = LN1(x): residual of the FFN block (kept in xs, or parked in global when xs is about to be reused by
@@ -266,14 +267,14 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
 #pragma unroll 8
         for (int r = 0; r < kRowsPer; r++) {
           const int row = nr0 + r;
-          const float y = ln_apply(xs[row * XS + nf], stats[row], stats[R + row], g, b);
+          const float y = ln_apply_t<kFast>(xs[row * XS + nf], stats[row], stats[R + row], g, b);
           if constexpr (L::kParkY) {
             const int grow = row0 + row;
             if (grow < a.M) a.y_park[static_cast<size_t>(grow) * E + nf] = y;
           } else {
             xs[row * XS + nf] = y;
           }
-          dst[r * 128 + xn[r & 7]] = static_cast<uint8_t>(quantize1(y, a.aq_1));
+          dst[r * 128 + xn[r & 7]] = static_cast<uint8_t>(quantize<kFast>(y, a.aq_1));
         }
       }
       fence_proxy_async();
@@ -302,9 +303,9 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
         uint8_t* dst = opnd_f + fs * kOpK + cg * RPW * 128;
 #pragma unroll
         for (int r = 0; r < RPW; r++) {
-          float y = dequant1(static_cast<int>(v[r]), a.um_1, pb);
+          float y = dequant<kFast>(static_cast<int>(v[r]), a.um_1, pb);
           y = fmaxf(y, 0.0f);  // std::max<float>(0, a), TensorOps.cc:163 (NaN -> 0 and -0 -> +0 either way)
-          dst[r * 128 + xo[r & 7]] = static_cast<uint8_t>(quantize1(y, a.aq_2));
+          dst[r * 128 + xo[r & 7]] = static_cast<uint8_t>(quantize<kFast>(y, a.aq_2));
         }
         fence_proxy_async();
         __syncwarp();
@@ -336,12 +337,13 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
         tmem_ld_wait();
 #pragma unroll
         for (int r = 0; r < RPW; r++)
-          xs[(cg * RPW + r) * XS + f] = __fadd_rn(dequant1(static_cast<int>(v[r]), a.um_2, pb), yv[r]);
+          xs[(cg * RPW + r) * XS + f] = __fadd_rn(dequant<kFast>(static_cast<int>(v[r]), a.um_2, pb), yv[r]);
       }
       tc_fence_before();
       named_bar_sync(1, kEpiThreads);
       if (et == 0) SB_TRACE(a, 10);
-      if (et < R) ln_stats_row<E>(xs + et * XS, &stats[et], &stats[R + et], a.eps);
+      if constexpr (kFast) ln_stats_fast<E, R>(xs, stats, a.eps, ew, lane);
+      else if (et < R) ln_stats_row<E>(xs + et * XS, &stats[et], &stats[R + et], a.eps);
       named_bar_sync(1, kEpiThreads);
       if (et == 0) SB_TRACE(a, 11);
       {
@@ -361,12 +363,12 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
 #pragma unroll 4
         for (int r = 0; r < rows_here; r++) {
           const int row = nr0 + r;
-          const float z = ln_apply(xs[row * XS + nf], stats[row], stats[R + row], g, b);
+          const float z = ln_apply_t<kFast>(xs[row * XS + nf], stats[row], stats[R + row], g, b);
           const size_t o = static_cast<size_t>(row) * E;
           if (zo) zo[o] = z;
 #pragma unroll
           for (int k = 0; k < 4; k++)
-            if (zp[k]) zp[k][o] = static_cast<uint8_t>(quantize1(z, za[k]) - zsub[k]);
+            if (zp[k]) zp[k][o] = static_cast<uint8_t>(quantize<kFast>(z, za[k]) - zsub[k]);
         }
       }
       if (et == 0) SB_TRACE(a, 12);
@@ -380,13 +382,13 @@ __global__ void __launch_bounds__(kThreads, 1) rows_ffn_kernel(const __grid_cons
   if (warp == 2) tmem_dealloc<512>(tmem);
 }
 
-template <int E, int F, int R>
+template <int E, int F, int R, bool kFast>
 int launch(const RowsFfnArgs& a, cudaStream_t stream) {
   using L = FfnPlan<E, F, R>;
   const int tiles = (a.M + R - 1) / R;
   if (tiles == 0) return 0;
   if (L::kParkY && a.y_park == nullptr) return 1;
-  auto kern = rows_ffn_kernel<E, F, R>;
+  auto kern = rows_ffn_kernel<E, F, R, kFast>;
   ensure_dyn_smem(kern, L::total);
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
@@ -397,10 +399,10 @@ int launch(const RowsFfnArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
-int launch_rows_ffn(const RowsFfnArgs& a, int E, int F, int rows_per_tile, cudaStream_t stream) {
-  if (E == 256 && F == 1536 && rows_per_tile == 32) return launch<256, 1536, 32>(a, stream);
-  if (E == 256 && F == 1536 && rows_per_tile == 128) return launch<256, 1536, 128>(a, stream);
-  if (E == 512 && F == 2048 && rows_per_tile == 32) return launch<512, 2048, 32>(a, stream);
+int launch_rows_ffn(const RowsFfnArgs& a, int E, int F, int rows_per_tile, bool fast, cudaStream_t stream) {
+  if (E == 256 && F == 1536 && rows_per_tile == 32) return fast ? launch<256, 1536, 32, true>(a, stream) : launch<256, 1536, 32, false>(a, stream);
+  if (E == 256 && F == 1536 && rows_per_tile == 128) return fast ? launch<256, 1536, 128, true>(a, stream) : launch<256, 1536, 128, false>(a, stream);
+  if (E == 512 && F == 2048 && rows_per_tile == 32) return fast ? launch<512, 2048, 32, true>(a, stream) : launch<512, 2048, 32, false>(a, stream);
   return 1;
 }
 

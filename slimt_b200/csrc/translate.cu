@@ -66,6 +66,7 @@ Context* Model::lane(size_t i) {
     if (c->init(ctx->device)) return nullptr;
     lanes.push_back(std::move(c));
   }
+  lanes[i - 1]->fast = ctx->fast;  // lanes compute in the arithmetic mode of the model's own context
   return lanes[i - 1].get();
 }
 
