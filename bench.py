@@ -296,8 +296,8 @@ def main():
     ap.add_argument("--workload", default="tiny_shortlist", choices=sorted(WORKLOADS),
                     help="tiny_shortlist = the headline (BASELINE.json configs[1]); the others are its remaining GPU configs")
     ap.add_argument("--math", default="both", choices=["both", "fast", "exact"],
-                    help="arithmetic mode(s) to measure; with `both` the top-level keys are the tolerance mode's and the "
-                         "bit-exact mode's numbers are under `exact`")
+                    help="arithmetic mode(s) to measure; with `both` the top-level keys are the bit-exact mode's and the "
+                         "tolerance mode's numbers are reported beside them under `fast`")
     ap.add_argument("--profiler-range", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -484,7 +484,7 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    modes = ["fast", "exact"] if args.math == "both" else [args.math]
+    modes = ["exact", "fast"] if args.math == "both" else [args.math]
     res = {}
     for i, mode in enumerate(modes):
         res[mode] = measure(mode, sampler if i == 0 else None)
@@ -509,10 +509,10 @@ def main():
         "batches_per_step": len(resident),
     }
     out["config"]["math"] = (
+        "exact = every float bit-identical to the reference CPU path (intgemm, exact int32 accumulation); the default and the "
+        "mode all top-level numbers are measured in" if head["math"] == "exact" else
         "fast = tolerance mode: f32/int32 arithmetic throughout, FMA-contracted dequantisation, tree-reduced LayerNorm sums, "
-        "ex2/rcp softmax and sigmoid, integer argmax proxy; held to BASELINE.json's bars (logits rtol 1e-3, >= 99 % greedy "
-        "tokens: tests/test_gpu_fast_mode.py).  exact = bit-identical to the reference CPU path (every other GPU test)."
-        if head["math"] == "fast" else "exact = bit-identical to the reference CPU path")
+        "ex2/rcp softmax and sigmoid, integer argmax proxy (tests/test_gpu_fast_mode.py says what that costs in agreement)")
     if len(modes) == 2:
         other = res[modes[1]]
         out[other["math"]] = {k: other[k] for k in ("value", "ms_per_step", "e2e", "gpu_launches", "roofline", "int8_gemm_summary", "kernels")}
@@ -523,7 +523,9 @@ def main():
         sent_total = sum(x.shape[1] for x in head["_tokens"])
         out["fast_vs_exact"] = {"step_tokens_equal": round(same / max(1, total), 6), "sentences_identical": round(sent_same / max(1, sent_total), 6),
                                 "note": "greedy free-running decode of this run's own batch in both modes (rank 0); exact mode equals the "
-                                        "reference token for token (tests/test_gpu_large_golden.py)"}
+                                        "reference token for token (tests/test_gpu_large_golden.py); in tolerance mode a few-ulp "
+                                        "difference occasionally moves one int8 operand by one step, which this random-init model "
+                                        "amplifies, and a sentence that differs once differs in all later tokens"}
 
     if not args.no_cpu_baseline:
         if os.path.exists(REF_BIN):

@@ -406,6 +406,23 @@ int Model::load(Context* c, const void* bin, size_t bytes, int enc_layers, int d
     SB_CUDA(cudaMalloc(&out.ipb6, 4ul * ((V + 255) / 256 * 256)));
     owned.push_back(out.ipb6);
     launch_out_ipb(out.c127, out.pb, out.um, V, out.ipb6, c->stream);
+    {
+      const size_t vpad = static_cast<size_t>((V + 255) / 256 * 256);
+      int* d_flag = nullptr;
+      SB_CUDA(cudaMalloc(&out.ext, vpad * 128));
+      owned.push_back(out.ext);
+      SB_CUDA(cudaMalloc(&out.dshift, vpad * 4));
+      owned.push_back(out.dshift);
+      SB_CUDA(cudaMalloc(&d_flag, 4));
+      SB_CUDA(cudaMemsetAsync(d_flag, 0, 4, c->stream));
+      launch_out_ext(out.c127, out.pb, out.um, V, out.ext, out.dshift, d_flag, c->stream);
+      int flag = 0;
+      SB_CUDA(cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+      SB_CUDA(cudaStreamSynchronize(c->stream));
+      SB_CUDA(cudaFree(d_flag));
+      out.ext_ok = flag == 0;
+      if (ctx->make_map(&out.map_ext, out.ext, vpad, 128, 256)) return 1;
+    }
     SB_CUDA(cudaStreamSynchronize(c->stream));
     std::vector<float> pbh(V);
     SB_CUDA(cudaMemcpy(pbh.data(), out.pb, 4ul * V, cudaMemcpyDeviceToHost));
@@ -670,7 +687,7 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
   acc(4ul * max_steps * B);                        // step tokens
   if (a.forced) acc(4ul * max_steps * B);
   if (a.sentence_tokens) acc(4ul * max_steps * B);
-  if (use_sl) acc(4ul * Nout), acc(1ul * Nout * E), acc(4ul * Nout), acc(4ul * Nout), acc(4ul * (Nout / 32 + 1)), acc(4ul * (Nout + 256));
+  if (use_sl) acc(4ul * Nout), acc(1ul * Nout * E), acc(4ul * Nout), acc(4ul * Nout), acc(4ul * (Nout / 32 + 1)), acc(4ul * (Nout + 256)), acc(128ul * (Nout + 256)), acc(4ul * (Nout + 256)), acc(256);
   if (a.logits) acc(4ul * B * Nout);
   if (a.alignment) acc(4ul * max_steps * B * T);
   need += 64 * 256;
@@ -935,6 +952,13 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
   const int32_t* c127_out = m.out.c127;
   const float* dmax_out = m.out.dmax;
   const int32_t* ipb6_out = m.out.ipb6;
+  const int32_t* dshift_out = m.out.dshift;
+  CUtensorMap map_ext = m.out.map_ext;
+  static const bool out_legacy = [] {
+    const char* e = getenv("SLIMT_B200_OUT");  // SLIMT_B200_OUT=legacy keeps gemm_out.cu (A/B measurements, cross-checks)
+    return e && strcmp(e, "legacy") == 0;
+  }();
+  const bool out_ext = m.out.ext_ok && !out_legacy;
   if (use_sl) {
     if (a.device_io) {
       d_sl = a.shortlist;
@@ -959,11 +983,19 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
       launch_out_bounds(cs, pbs, m.out.um, Nout, dms, s);
     }
     int32_t* ips = c.take<int32_t>(static_cast<size_t>(Nout) + 256);
-    if (c.fast) {
+    uint8_t* exts = c.take<uint8_t>(128ul * (static_cast<size_t>(Nout) + 256));
+    int32_t* dss = c.take<int32_t>(static_cast<size_t>(Nout) + 256);
+    int* flag = c.take<int>(64);
+    if (out_ext) {
+      // a subset of columns whose offsets all fit the digits fits them too: the flag is not read back
+      LaunchScope ls(c, "out_bounds", 0, 140.0 * Nout);
+      launch_out_ext(cs, pbs, m.out.um, Nout, exts, dss, flag, s);
+      if (c.make_map(&map_ext, exts, static_cast<uint64_t>((Nout + 255) / 256 * 256), 128, 256)) return 1;
+    } else if (c.fast) {
       LaunchScope ls(c, "out_bounds", 0, 12.0 * Nout);
       launch_out_ipb(cs, pbs, m.out.um, Nout, ips, s);
     }
-    Wout = Ws, pb_out = pbs, c127_out = cs, dmax_out = dms, ipb6_out = ips;
+    Wout = Ws, pb_out = pbs, c127_out = cs, dmax_out = dms, ipb6_out = ips, dshift_out = dss;
   }
   CUtensorMap map_xq[2], map_zq[2], map_caq;  // u8 activation operands of the row-tile kernels, box {128 B, 32 rows}
   for (int i = 0; i < 2; i++) {
@@ -1092,8 +1124,12 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
     } else {
       const double Md = B, Nd = Nout, Kd = E;
       LaunchScope ls(c, "dec_gemm_out_argmax", 2.0 * Md * Nd * Kd, Md * Kd + Nd * Kd + 4.0 * Nd + 8.0 * Md);
-      if (launch_gemm_out_argmax(map_oq, map_wout, pb_out, c127_out, dmax_out, c.fast ? ipb6_out : nullptr, m.out.um,
-                                 m.out.eta, B, Nout, E, best, c.num_sms, s)) {
+      const int rc = out_ext ? launch_gemm_out_argmax_ext(map_oq, map_wout, map_ext, pb_out, dshift_out, m.out.um, c.fast, B,
+                                                          Nout, E, best, c.num_sms, s)
+                             : launch_gemm_out_argmax(map_oq, map_wout, pb_out, c127_out, dmax_out,
+                                                      c.fast ? ipb6_out : nullptr, m.out.um, m.out.eta, B, Nout, E, best,
+                                                      c.num_sms, s);
+      if (rc) {
         set_error("output GEMM: unsupported K " + std::to_string(E));
         return 1;
       }

@@ -124,6 +124,12 @@ struct DevWeight {
   float* dmax = nullptr;    // [ceil(N/32)]
   float eta = 0;            // slack covering the float roundings of the exact epilogue
   int32_t* ipb6 = nullptr;  // [ceil(N/256)*256] integer logit-proxy offsets (tolerance mode, gemm_out.cu)
+  // second-generation output GEMM (gemm_out_ext.cu): digit rows [ceil(N/256)*256][128], proxy -> accumulator shifts,
+  // and whether every column's offset fits the digits (otherwise gemm_out.cu is used)
+  uint8_t* ext = nullptr;
+  int32_t* dshift = nullptr;
+  CUtensorMap map_ext;
+  bool ext_ok = false;
 };
 
 struct DevLN {

@@ -76,4 +76,12 @@ int launch_gemm_out_argmax(const CUtensorMap& tma_a, const CUtensorMap& tma_b, c
                            const float* dmax, const int32_t* ipb6, float um, float eta, int M, int N, int K,
                            unsigned long long* best, int num_sms, cudaStream_t stream);
 
+// Second generation (gemm_out_ext.cu): the column offsets ride through the tensor core as an extra K = 32 block.
+// tma_e: the digit rows from launch_out_ext, u8 [ceil(N/256)*256][128] with box {128 B, 256 rows}; dshift from the
+// same call.  fast selects the tolerance-mode choice (integer proxy); otherwise the result is the exact first strict
+// maximum of the float logits.
+int launch_gemm_out_argmax_ext(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const CUtensorMap& tma_e, const float* pb,
+                               const int32_t* dshift, float um, bool fast, int M, int N, int K, unsigned long long* best,
+                               int num_sms, cudaStream_t stream);
+
 }  // namespace sb

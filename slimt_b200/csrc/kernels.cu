@@ -295,6 +295,43 @@ __global__ void out_ipb_kernel(const int32_t* __restrict__ c127, const float* __
   ipb6[n] = (static_cast<int32_t>(t) << 6) + (63 - (n & 63));
 }
 
+// Per output column n (gemm_out_ext.cu): ipb[n] = round(c127[n] + pb[n] / um) in double, written as 32 int8 digits
+// e[n][0..31] with sum_k a_k * e[n][k] = ipb[n] for a = (127 x 31, 1), one 128-byte row per column (the layout the
+// weight tile's TMA box uses; bytes 32..127 stay zero); dshift[n] = c127[n] - ipb[n] turns a proxy back into the
+// shifted accumulator of the exact formula.  Columns N .. n_pad - 1 are zero.  *overflow is set when some |ipb|
+// exceeds what the digits can hold (31 * 127 * 127 + 63).
+__global__ void out_ext_kernel(const int32_t* __restrict__ c127, const float* __restrict__ pb, float um, int N, int n_pad,
+                               uint8_t* __restrict__ ext, int32_t* __restrict__ dshift, int* __restrict__ overflow) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_pad) return;
+  uint4* row = reinterpret_cast<uint4*>(ext + static_cast<size_t>(n) * 128);
+  uint32_t w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+  int ds = 0;
+  if (n < N) {
+    double t = rint(static_cast<double>(c127[n]) + static_cast<double>(pb[n]) / static_cast<double>(um));
+    if (fabs(t) > 500093.0) {
+      atomicOr(overflow, 1);
+      t = fmin(fmax(t, -500093.0), 500093.0);
+    }
+    const int ipb = static_cast<int>(t);
+    int Q = static_cast<int>(rint(static_cast<double>(ipb) / 127.0));
+    if (Q > 3937) Q = 3937;
+    if (Q < -3937) Q = -3937;
+    const int r = ipb - 127 * Q;  // |r| <= 63 (<= 126 at the clamped ends, still an int8)
+    const int base = Q / 31, rem = Q - 31 * base;
+    const int step = rem > 0 ? 1 : -1, cnt = rem > 0 ? rem : -rem;
+    for (int k = 0; k < 32; k++) {
+      const int d = k < 31 ? base + (k < cnt ? step : 0) : r;
+      w[k >> 2] |= static_cast<uint32_t>(d & 0xff) << (8 * (k & 3));
+    }
+    ds = c127[n] - ipb;
+  }
+  row[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  row[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  for (int i = 2; i < 8; i++) row[i] = make_uint4(0u, 0u, 0u, 0u);
+  dshift[n] = ds;
+}
+
 __device__ __forceinline__ unsigned long long pack_best_k(float v, uint32_t idx) {
   if (v == 0.0f) v = 0.0f;
   uint32_t bits = __float_as_uint(v);
@@ -387,6 +424,13 @@ void launch_out_ipb(const int32_t* c127, const float* pb, float um, int N, int32
   const int n_pad = (N + 255) / 256 * 256;
   if (n_pad == 0) return;
   out_ipb_kernel<<<(n_pad + 255) / 256, 256, 0, stream>>>(c127, pb, um, N, n_pad, ipb6);
+}
+
+void launch_out_ext(const int32_t* c127, const float* pb, float um, int N, uint8_t* ext, int32_t* dshift, int* overflow,
+                    cudaStream_t stream) {
+  const int n_pad = (N + 255) / 256 * 256;
+  if (n_pad == 0) return;
+  out_ext_kernel<<<(n_pad + 127) / 128, 128, 0, stream>>>(c127, pb, um, N, n_pad, ext, dshift, overflow);
 }
 
 __global__ void transpose_u32_kernel(const uint32_t* __restrict__ src, int rows, int cols, uint32_t* __restrict__ dst,
