@@ -279,6 +279,83 @@ def run_reference_arm(args):
     return 0
 
 
+def run_single_process(args):
+    """One process, one Batcher, N GPUs: slimt_b200_translate_multi deals the request's batches to one model replica
+    per GPU (two lanes each).  This is the service shape of the reference's Async (Frontend.cc:207-227) and the
+    measurement of SURVEY.md section 8(e)'s scaling risk: ONE host feeding N GPUs.  `value` is end to end by
+    construction (host buffers in and out); strong scaling: the request is the same for every N."""
+    import ctypes
+    from slimt_b200 import capi
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    n_sent = args.sentences or WL["sentences"]
+    dims = wl_dims()
+    tmp = tempfile.mkdtemp(prefix="slimt_b200_sp_")
+    model_path = os.path.join(tmp, "model.bin")
+    synth.write_model(model_path, synth.make_params(dims, seed=MODEL_SEED))
+    fr, offs, lists = synth.make_shortlist(vocab=dims.vocab, frequent=100, best=100, seed=7)
+    sl_path = os.path.join(tmp, "lex.s2t.bin")
+    synth.write_shortlist(sl_path, fr, offs, lists, best=100)
+    t0 = time.perf_counter()
+    rng = np.random.RandomState(1000)
+    if isinstance(WL["length"], int):
+        lens = np.full(n_sent, WL["length"], dtype=np.int64)
+    else:
+        lens = rng.randint(WL["length"][0], WL["length"][1] + 1, size=n_sent).astype(np.int64)
+    h_offsets = np.zeros(n_sent + 1, dtype=np.uint64)
+    h_offsets[1:] = np.cumsum(lens)
+    h_tokens = rng.randint(1, dims.vocab, size=int(h_offsets[-1])).astype(np.uint32)
+    h_tokens[(h_offsets[1:] - 1).astype(np.int64)] = synth.EOS_ID  # every sentence ends in EOS
+    gen_s = time.perf_counter() - t0
+    blob = open(model_path, "rb").read()
+    ctxs = [capi.Context(i) for i in range(args.gpus)]
+    for c in ctxs:
+        c.set_math(args.math == "fast")
+    models = [capi.Model(c, blob) for c in ctxs]
+    sl_bin = open(sl_path, "rb").read() if WL["shortlist"] else None
+    sl_buf = (ctypes.c_char * len(sl_bin)).from_buffer_copy(sl_bin) if sl_bin is not None else None
+    max_steps = max(1, int(np.float32(LIMIT) * np.float32(lens.max())))
+    out_tokens = np.zeros(int(n_sent) * max_steps, dtype=np.uint32)
+    out_offsets = np.zeros(n_sent + 1, dtype=np.uint64)
+    sampler = ClockSampler(0)
+    sampler.start()
+    # warm-up: a slice of the request, enough to build every lane's workspace and touch every kernel variant
+    warm = min(n_sent, 4096 * args.gpus)
+    for _ in range(max(1, args.warmup - 2)):
+        models[0].translate_flat(h_tokens[:int(h_offsets[warm])], h_offsets[:warm + 1], WL["max_words"], LIMIT, sl_buf,
+                                 out_tokens, out_offsets[:warm + 1], replicas=models)
+    sampler.mark_begin()
+    secs, toks, st = 0.0, 0, None
+    steps = max(1, args.steps)
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        _, _, st = models[0].translate_flat(h_tokens, h_offsets, WL["max_words"], LIMIT, sl_buf, out_tokens, out_offsets,
+                                            replicas=models)
+        secs += time.perf_counter() - t0
+        toks += st["target_tokens"]
+    sampler.mark_end()
+    clocks = sampler.stop()
+    cfg = workload_config()
+    cfg["sentences_per_gpu"] = None
+    cfg["sentences"] = int(n_sent)
+    cfg["sharding"] = ("one process: one Batcher, batches dealt to one replica per GPU (slimt_b200_translate_multi), two lanes per "
+                       "replica; no collective")
+    cfg["l2"] = "inputs larger than L2 (a fresh batch every forward pass)"
+    value = toks / secs
+    out = {"metric": "target_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * secs / steps, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "int8", "data": "synthetic", "config": cfg, "clocks": clocks, "math": args.math,
+           "mode": "single-process", "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": st["h2d_bytes"],
+                                             "d2h_bytes_per_step": st["d2h_bytes"],
+                                             "api": "slimt_b200_translate_multi (host buffers, one call per step)"},
+           "gpu_launches": st["kernel_launches"] * steps, "batches_per_step": st["batches"],
+           "device_ms_longest_replica": st["device_ms"], "host_cores": os.cpu_count(),
+           "input_generation_s": round(gen_s, 2)}
+    os.write(json_fd, (json.dumps(out) + "\n").encode())
+    return 0
+
+
 def workload_config():
     return {"workload": WL["desc"], "sentences_per_gpu": WL["sentences"], "src_len": WL["length"], "limit_factor": LIMIT,
             "max_words": WL["max_words"], "l2": "flushed between timed steps (256 MiB memset)",
@@ -298,6 +375,10 @@ def main():
     ap.add_argument("--math", default="both", choices=["both", "fast", "exact"],
                     help="arithmetic mode(s) to measure; with `both` the top-level keys are the bit-exact mode's and the "
                          "tolerance mode's numbers are reported beside them under `fast`")
+    ap.add_argument("--single-process", action="store_true",
+                    help="serve ONE request with --gpus replicas from this process (slimt_b200_translate_multi) instead of "
+                         "one process per GPU; strong scaling")
+    ap.add_argument("--sentences", type=int, default=0, help="with --single-process: sentences in the request (default: the workload's)")
     ap.add_argument("--profiler-range", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -305,6 +386,10 @@ def main():
     WL = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.single_process:
+        if args.math == "both":
+            args.math = "exact"
+        return run_single_process(args)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

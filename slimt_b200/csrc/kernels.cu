@@ -208,17 +208,21 @@ __global__ void ssru_ln_kernel(const float* __restrict__ f, const float* __restr
 }
 
 // ------------------------------------------------------------------ step bookkeeping
-__global__ void finalize_step_kernel(unsigned long long* __restrict__ best, const uint32_t* __restrict__ shortlist,
-                                     const uint32_t* __restrict__ forced, int step, uint32_t* __restrict__ step_tokens,
-                                     uint8_t* __restrict__ done, uint32_t* __restrict__ tgt_len,
-                                     int* __restrict__ n_done, uint32_t eos_id,
-                                     const int8_t* __restrict__ emb_q, float inv_qm, float sqrt_e,
-                                     const float* __restrict__ pos0, int B, int E, float* __restrict__ x, QuantOuts q) {
-  __shared__ uint32_t s_next;
-  const int b = blockIdx.x;
+// Warp = one sentence row, eight rows per block: lane 0 does the row's bookkeeping and broadcasts the next input word,
+// the warp then builds that word's decoder input.  (One 64-thread block per row -- the first version -- spent most of
+// its 10.9 us at B = 4096 launching 4096 tiny blocks.)
+__global__ void __launch_bounds__(256) finalize_step_kernel(
+    unsigned long long* __restrict__ best, const uint32_t* __restrict__ shortlist, const uint32_t* __restrict__ forced,
+    int step, uint32_t* __restrict__ step_tokens, uint8_t* __restrict__ done, uint32_t* __restrict__ tgt_len,
+    int* __restrict__ n_done, uint32_t eos_id, const int8_t* __restrict__ emb_q, float inv_qm, float sqrt_e,
+    const float* __restrict__ pos0, int B, int E, float* __restrict__ x, QuantOuts q) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   pdl_launch_dependents();
   pdl_wait();
-  if (threadIdx.x == 0) {
+  if (b >= B) return;
+  uint32_t tok = 0;
+  if (lane == 0) {
     const unsigned long long packed = best[b];
     const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(packed & 0xFFFFFFFFull);
     const uint32_t word = shortlist ? shortlist[idx] : idx;
@@ -231,11 +235,10 @@ __global__ void finalize_step_kernel(unsigned long long* __restrict__ best, cons
       }
     }
     best[b] = 0ull;
-    s_next = forced ? forced[static_cast<size_t>(step) * B + b] : word;
+    tok = forced ? forced[static_cast<size_t>(step) * B + b] : word;
   }
-  __syncthreads();
-  const uint32_t tok = s_next;
-  for (int e = threadIdx.x * 4; e < E; e += blockDim.x * 4) {
+  tok = __shfl_sync(0xffffffffu, tok, 0);
+  for (int e = lane * 4; e < E; e += 128) {
     const char4 c = *reinterpret_cast<const char4*>(emb_q + static_cast<size_t>(tok) * E + e);
     const float4 ps = *reinterpret_cast<const float4*>(pos0 + e);
     float y[4];
@@ -404,7 +407,7 @@ void launch_finalize_step(unsigned long long* best, const uint32_t* shortlist, c
                           const int8_t* emb_q, float inv_qm, float sqrt_e, const float* pos0, int B, int E, float* x,
                           QuantOuts q, cudaStream_t stream) {
   if (B == 0) return;
-  launch_pdl(finalize_step_kernel, dim3(B), dim3(64), 0, stream, best, shortlist, forced, step, step_tokens, done, tgt_len,
+  launch_pdl(finalize_step_kernel, dim3((B + 7) / 8), dim3(256), 0, stream, best, shortlist, forced, step, step_tokens, done, tgt_len,
              n_done, eos_id, emb_q, inv_qm, sqrt_e, pos0, B, E, x, q);
 }
 
