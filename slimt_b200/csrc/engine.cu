@@ -1039,6 +1039,13 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
         k.um_f = L.rnn_wf.um, k.um_w = L.rnn_w.um, k.um_q = L.ctx.q.um;
         k.aq_q = L.ctx.q.aq;
         k.x = in_f, k.state = state[l];
+        if (l == 0 && step > 0) {  // close the previous step and embed its words in this kernel's front
+          k.embed = 1, k.prev_step = step - 1;
+          k.best = best, k.shortlist = d_sl, k.forced = d_forced, k.step_tokens = d_steps;
+          k.done = done, k.tgt_len = tgt_len, k.n_done = counters, k.eos_id = m.eos_id;
+          k.emb_q = m.emb_q, k.inv_qm = m.inv_qm, k.sqrt_e = m.sqrt_e, k.pos0 = m.pos;
+          k.aq_xf = L.rnn_wf.aq, k.aq_xw = L.rnn_w.aq;
+        }
         k.ln_scale = L.rnn_ln.scale, k.ln_bias = L.rnn_ln.bias, k.eps = 1e-6f;
         k.h_out = hb, k.q_out = qd, k.M = B;
         if (trace_buf && step == 3 && l == 0) k.trace = trace_buf;
@@ -1134,34 +1141,39 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
         return 1;
       }
     }
-    {
-      QuantOuts q = qouts();
-      qadd(q, xq[0], m.dec[0].rnn_wf.aq), qadd(q, xq[1], m.dec[0].rnn_w.aq);
-      LaunchScope ls(c, "dec_finalize_embed", 0, 7.0 * B * E + 20.0 * B);
-      launch_finalize_step(best, d_sl, d_forced, step, d_steps, done, tgt_len, counters, m.eos_id, m.emb_q, m.inv_qm,
-                           m.sqrt_e, m.pos, B, E, xd, q, s);
-    }
+    // The step's bookkeeping (argmax -> word, record(), EOS flags) and the next step's input embedding are done by the
+    // FRONT of the next step's first kernel (dec_ssru_kernel with embed set); the last executed step is closed by the
+    // stand-alone kernel after the loop.
     executed = step + 1;
-    // Model.cc:161: the loop stops once every sentence has produced EOS.  The done-counter of each step is
-    // copied to a pinned slot behind an event; the host looks at the slot from kLag steps ago, so the
-    // stream always holds a few queued steps and is never drained (extra steps only produce discarded tokens).
-    {
-      constexpr int kSlots = 8, kLag = 4;
-      const int slot = step % kSlots;
-      SB_CUDA(cudaMemcpyAsync(&c.done_slots[slot], counters, 4, cudaMemcpyDeviceToHost, s));
-      SB_CUDA(cudaEventRecord(c.done_events[slot], s));
+    // Model.cc:161: the loop stops once every sentence has produced EOS.  Every second step the done-counter is copied
+    // to a pinned slot behind an event and the host looks at the previous copy, so the stream always holds a few
+    // queued steps and is never drained (extra steps only produce discarded tokens); the steps in between stay
+    // chained by programmatic dependent launch.
+    if ((step & 1) == 1) {
+      constexpr int kSlots = 8;
+      const int poll = step >> 1;
+      SB_CUDA(cudaMemcpyAsync(&c.done_slots[poll % kSlots], counters, 4, cudaMemcpyDeviceToHost, s));
+      SB_CUDA(cudaEventRecord(c.done_events[poll % kSlots], s));
       c.d2h_bytes += 4;
-      if (step >= kLag) {
-        const int old = (step - kLag) % kSlots;
+      if (poll >= 1) {
+        const int old = (poll - 1) % kSlots;
         SB_CUDA(cudaEventSynchronize(c.done_events[old]));
-        host_done = c.done_slots[old];
-        if (host_done >= B) break;
+        if (c.done_slots[old] >= B) break;
       }
     }
   }
-  if (executed > 0 && host_done < B) {
+  if (executed > 0) {
+    QuantOuts q = qouts();
+    qadd(q, xq[0], m.dec[0].rnn_wf.aq), qadd(q, xq[1], m.dec[0].rnn_w.aq);
+    {
+      LaunchScope ls(c, "dec_finalize_embed", 0, 7.0 * B * E + 20.0 * B);
+      launch_finalize_step(best, d_sl, d_forced, executed - 1, d_steps, done, tgt_len, counters, m.eos_id, m.emb_q, m.inv_qm,
+                           m.sqrt_e, m.pos, B, E, xd, q, s);
+    }
+    SB_CUDA(cudaMemcpyAsync(&c.done_slots[0], counters, 4, cudaMemcpyDeviceToHost, s));
+    c.d2h_bytes += 4;
     SB_CUDA(cudaStreamSynchronize(s));
-    host_done = c.done_slots[(executed - 1) % 8];
+    host_done = c.done_slots[0];
   }
 
   if (trace_buf) {

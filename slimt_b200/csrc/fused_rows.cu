@@ -34,7 +34,7 @@ struct SsruSmem {
   static constexpr int total = tmem_slot + 16 + 1024;
 };
 
-template <int E, bool kFast>
+template <int E, bool kFast, bool kEmbed>
 __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_constant__ DecSsruArgs a) {
   using L = SsruSmem<E>;
   constexpr int EK = E / 128, EM = E / 128;
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < L::kStages; s++) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
-    mbar_init(x_full, 1);
+    mbar_init(x_full, kEmbed ? kEpiWarps : 1);  // kEmbed: the epilogue warps build the x operands themselves
     mbar_init(g0_done, 1);
     mbar_init(hq_ready, kEpiWarps);
     mbar_init(g1_done, 1);
@@ -117,16 +117,19 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
     const uint32_t tph = iter & 1;
     if (warp == 0) {
       if (leader) {
-        mbar_expect_tx(x_full, 2 * EK * kOpK);
-        for (int kb = 0; kb < EK; kb++) {
-          tma_load_2d(opnd_xf + kb * kOpK, &a.map_xf, x_full, kb * 128, row0);
-          tma_load_2d(opnd_xw + kb * kOpK, &a.map_xw, x_full, kb * 128, row0);
+        if constexpr (!kEmbed) {
+          mbar_expect_tx(x_full, 2 * EK * kOpK);
+          for (int kb = 0; kb < EK; kb++) {
+            tma_load_2d(opnd_xf + kb * kOpK, &a.map_xf, x_full, kb * 128, row0);
+            tma_load_2d(opnd_xw + kb * kOpK, &a.map_xw, x_full, kb * 128, row0);
+          }
         }
         load_weights(iter == 0 && SB_PRE_SSRU ? L::kStages : 0, 1 << 30);
       }
     } else if (warp == 1) {
       if (leader) {
         mbar_wait(x_full, tph);
+        if constexpr (kEmbed) tc_fence_after();
         SB_TRACE(a, 2);
         for (int mb = 0; mb < EM; mb++)
           for (int kb = 0; kb < EK; kb++) cons.mma(tmem_f + mb * kR, opnd_xf + kb * kOpK, kb == 0);
@@ -156,6 +159,50 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
       // ---- highway + relu + residual (slimt/Modules.cc:218-232, TensorOps.cc:662-682) -> xs
       {
         float st[EM][8], xv[EM][8];  // previous cell state and layer input of this thread's (rows, features)
+        if constexpr (kEmbed) {
+          // the previous step's bookkeeping for the tile's rows (finalize_step_kernel's, thread = row), then the
+          // words' embedding rows -> x (registers) and its two quantised operands (shared memory, UMMA layout)
+          uint32_t* s_tok = reinterpret_cast<uint32_t*>(stats);  // free until the LayerNorm statistics
+          if (et < kR) {
+            const int b = row0 + et;
+            uint32_t tok = 0;
+            if (b < a.M) {
+              const unsigned long long packed = a.best[b];
+              const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(packed & 0xFFFFFFFFull);
+              const uint32_t word = a.shortlist ? a.shortlist[idx] : idx;
+              a.step_tokens[static_cast<size_t>(a.prev_step) * a.M + b] = word;
+              if (!a.done[b]) {  // record(), slimt/Model.cc:127-137: append unless already finished
+                a.tgt_len[b] += 1;
+                if (word == a.eos_id) {
+                  a.done[b] = 1;
+                  atomicAdd(a.n_done, 1);
+                }
+              }
+              a.best[b] = 0ull;
+              tok = a.forced ? a.forced[static_cast<size_t>(a.prev_step) * a.M + b] : word;
+            }
+            s_tok[et] = tok;
+          }
+          named_bar_sync(1, kEpiThreads);
+#pragma unroll
+          for (int mb = 0; mb < EM; mb++) {
+            const int f = mb * 128 + q * 32 + lane;
+            const float ps = a.pos0[f];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+              const int row = rq * 8 + r;
+              const float w = static_cast<float>(a.emb_q[static_cast<size_t>(s_tok[row]) * E + f]);
+              const float y = __fadd_rn(__fmul_rn(__fmul_rn(w, a.inv_qm), a.sqrt_e), ps);
+              xv[mb][r] = y;
+              const uint32_t off = opnd_off<kR>(row, f);
+              opnd_xf[off] = static_cast<uint8_t>(quantize1(y, a.aq_xf));
+              opnd_xw[off] = static_cast<uint8_t>(quantize1(y, a.aq_xw));
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(x_full);
+        }
 #pragma unroll
         for (int mb = 0; mb < EM; mb++) {
 #pragma unroll
@@ -163,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
             const int grow = row0 + rq * 8 + r;
             const size_t o = static_cast<size_t>(grow < a.M ? grow : 0) * E + mb * 128 + q * 32 + lane;
             st[mb][r] = a.state[o];
-            xv[mb][r] = a.x[o];
+            if constexpr (!kEmbed) xv[mb][r] = a.x[o];
           }
         }
         if (et == 0) SB_TRACE(a, 14);
@@ -258,13 +305,17 @@ int launch_rows(Kern kern, const Args& a, size_t smem, cudaStream_t stream) {
 
 }  // namespace
 
+template <int E>
+int launch_ssru_e(const DecSsruArgs& a, bool fast, cudaStream_t stream) {
+  constexpr size_t smem = SsruSmem<E>::total;
+  if (a.embed)
+    return fast ? launch_rows(dec_ssru_kernel<E, true, true>, a, smem, stream) : launch_rows(dec_ssru_kernel<E, false, true>, a, smem, stream);
+  return fast ? launch_rows(dec_ssru_kernel<E, true, false>, a, smem, stream) : launch_rows(dec_ssru_kernel<E, false, false>, a, smem, stream);
+}
+
 int launch_dec_ssru(const DecSsruArgs& a, int E, bool fast, cudaStream_t stream) {
-  if (E == 256)
-    return fast ? launch_rows(dec_ssru_kernel<256, true>, a, SsruSmem<256>::total, stream)
-                : launch_rows(dec_ssru_kernel<256, false>, a, SsruSmem<256>::total, stream);
-  if (E == 512)
-    return fast ? launch_rows(dec_ssru_kernel<512, true>, a, SsruSmem<512>::total, stream)
-                : launch_rows(dec_ssru_kernel<512, false>, a, SsruSmem<512>::total, stream);
+  if (E == 256) return launch_ssru_e<256>(a, fast, stream);
+  if (E == 512) return launch_ssru_e<512>(a, fast, stream);
   return 1;
 }
 

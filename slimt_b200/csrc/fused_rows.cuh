@@ -63,6 +63,24 @@ struct DecSsruArgs {
   float* q_out;                        // f32 [M][E]
   int M;
   long long* trace;                    // optional phase timestamps, as above
+  // ---- layer 0 from the second step on (embed != 0): the kernel's front does what finalize_step_kernel does for the
+  // PREVIOUS step -- packed argmax -> word id (through the shortlist), record into step_tokens[prev_step][M], EOS
+  // bookkeeping (Model.cc:127-137), re-arm `best` -- and builds this step's input from the word's embedding row
+  // (* sqrt(E) + position-0 signal; quirk Q1) straight into the operand tiles: x, map_xf and map_xw are then unused.
+  int embed;
+  int prev_step;
+  unsigned long long* best;
+  const uint32_t* shortlist;           // or null
+  const uint32_t* forced;              // teacher forcing [steps][M] or null
+  uint32_t* step_tokens;
+  uint8_t* done;
+  uint32_t* tgt_len;
+  int* n_done;
+  uint32_t eos_id;
+  const int8_t* emb_q;                 // stored embedding [V][E]
+  float inv_qm, sqrt_e;
+  const float* pos0;                   // position-0 signal [E]
+  float aq_xf, aq_xw;                  // a_quant of Wf / W (quantise x)
 };
 
 // E = 256, F = 1536 (tiny) and E = 512, F = 2048 (base) are built.  Returns nonzero when unsupported.
