@@ -727,9 +727,15 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
   CUtensorMap map_attn_q;  // u8 [R][E], box {128 B, 128 rows}: operand of the encoder's row-tile kernel
   if (c.make_map(&map_attn_q, attn_q, R, E, 128)) return 1;
 
-  // SLIMT_B200_SELFATTN=split keeps the projections and the attention as separate kernels (parity cross-check)
+  // SLIMT_B200_SELFATTN=split keeps the projections and the attention as separate kernels (parity cross-check);
+  // =rowwise additionally takes the first-generation one-thread-per-query kernel instead of the tiled one
   const char* sa_env = getenv("SLIMT_B200_SELFATTN");
-  const bool attn_fused = enc_attention_supported(E, H, dh, T) && !(sa_env && strcmp(sa_env, "split") == 0);
+  // the tiled kernel's 64-query x 128-key tiles pay off from T > 64 (mixed lengths: 15.9 -> 8.5 ms per layer of a
+  // 1M-word batch); at T <= 64 with head size 64 (base) half of every tile is idle and the row-wise kernel is faster
+  // (666 vs 1149 us per layer at 4096 x 32); SLIMT_B200_SELFATTN=tiled forces the tiled kernel (parity cross-check)
+  const bool attn_rowwise = (sa_env && strcmp(sa_env, "rowwise") == 0) || (T <= 64 && !(sa_env && strcmp(sa_env, "tiled") == 0));
+  const bool attn_fused = enc_attention_supported(E, H, dh, T) &&
+                          !(sa_env && (strcmp(sa_env, "split") == 0 || strcmp(sa_env, "rowwise") == 0 || strcmp(sa_env, "tiled") == 0));
   CUtensorMap map_qa[3];
   if (attn_fused)
     for (int i = 0; i < 3; i++)
@@ -790,7 +796,8 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
       QuantOuts q = qouts();
       qadd(q, attn_q, L.self.o.aq);
       LaunchScope ls(c, "enc_self_attention", 0, 13.0 * R * E);
-      if (launch_self_attention(Qb, Kb, Vb, d_lengths, B, T, H, dh, nullptr, q, s)) {
+      if (attn_rowwise ? launch_self_attention(Qb, Kb, Vb, d_lengths, B, T, H, dh, nullptr, q, s)
+                       : launch_self_attention_tiled(Qb, Kb, Vb, d_lengths, B, T, H, dh, nullptr, q, s)) {
         set_error("self-attention: unsupported head size " + std::to_string(dh));
         return 1;
       }

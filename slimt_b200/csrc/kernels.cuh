@@ -30,6 +30,11 @@ void launch_quantize(const float* x, size_t n, QuantOuts q, cudaStream_t stream)
 int launch_self_attention(const float* Q, const float* K, const float* V, const uint32_t* lengths, int B, int T,
                            int H, int dh, float* out_f32, QuantOuts q, cudaStream_t stream);
 
+// The same operation as a register-tiled kernel (self_attention_tiled.cu): 64 query rows of one (sentence, head) per
+// block, every output still one sequential chain.  The default for every shape the fused encoder kernel does not take.
+int launch_self_attention_tiled(const float* Q, const float* K, const float* V, const uint32_t* lengths, int B, int T,
+                                int H, int dh, float* out_f32, QuantOuts q, cudaStream_t stream);
+
 // Decoder cross-attention for one query row per sentence over cached K,V [B][S][E] (cross_attention.cu).
 // mapK/mapV: f32 tensor maps over [B*S][E] with box {32 floats, cross_attention_box_rows(S)}, 128B swizzle.
 // attn_head0 (optional) receives head 0's probabilities [B][S] (alignment, slimt/Model.cc:84-108).

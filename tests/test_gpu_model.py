@@ -112,6 +112,29 @@ def test_fused_encoder_attention_equals_split_path(tiny_gpu, shape, monkeypatch)
     assert np.array_equal(fused["logits"], split["logits"])
 
 
+@pytest.mark.parametrize("shape", [(5, 70), (3, 129), (2, 256), (9, 33), (40, 8), (3, 200)])
+def test_tiled_self_attention_equals_rowwise_kernel(tiny_gpu, shape, monkeypatch):
+    """The split path's attention kernel exists twice: the register-tiled one (self_attention_tiled.cu: 64 query rows
+    per block, partial key tiles, sentences straddling query blocks) and the first one-thread-per-query kernel.  Same
+    chains, so the same bits -- and both equal the oracle."""
+    m, orc = tiny_gpu
+    B, T = shape
+    sents = synth.make_sentences(B, (1, T), seed=13 * B + T)
+    sents[0] = synth.make_sentences(1, T, seed=2)[0]
+    sents[-1] = synth.make_sentences(1, max(1, T - 1), seed=3)[0]
+    tokens, lengths = util.pad_batch(sents)
+    monkeypatch.setenv("SLIMT_B200_SELFATTN", "tiled")
+    tiled = m.forward(tokens, lengths, want_encoder=True)
+    monkeypatch.setenv("SLIMT_B200_SELFATTN", "rowwise")
+    rowwise = m.forward(tokens, lengths, want_encoder=True)
+    monkeypatch.delenv("SLIMT_B200_SELFATTN")
+    valid = np.arange(T)[None, :] < np.asarray(lengths)[:, None]
+    assert np.array_equal(tiled["encoder_out"][valid], rowwise["encoder_out"][valid])
+    assert np.array_equal(tiled["step_tokens"], rowwise["step_tokens"])
+    ref = orc.forward(tokens, lengths, keep=True)
+    assert np.array_equal(tiled["encoder_out"][valid], ref["encoder_out"][valid])
+
+
 def test_forward_with_shortlist(tiny_gpu, shortlist_assets):
     m, orc = tiny_gpu
     fr, offs, lists = shortlist_assets[1]
