@@ -295,13 +295,9 @@ __global__ void __launch_bounds__(kThreads) gemm_i8_kernel(const __grid_constant
 
 template <int BN, int STAGES, int EPI>
 void launch_one(const GemmBatch& b, int n_problems, cudaStream_t stream) {
-  static bool configured = false;
   const size_t smem = gemm_smem_bytes(BN, STAGES);
   auto kern = gemm_i8_kernel<BN, STAGES, EPI>;
-  if (!configured) {
-    ensure_dyn_smem(kern, smem);
-    configured = true;
-  }
+  ensure_dyn_smem(kern, smem);  // per (device, kernel): a process may drive several GPUs
   dim3 grid((b.N + BN - 1) / BN, (b.M + kBM - 1) / kBM, n_problems);
   kern<<<grid, kThreads, smem, stream>>>(b);
 }

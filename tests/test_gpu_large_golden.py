@@ -126,6 +126,26 @@ def test_replicas_and_lanes_do_not_change_the_output(gpu_ctx, tiny_model, shortl
     a.close(), b.close()
 
 
+def test_replicas_on_two_gpus_equal_one(gpu_ctx, tiny_model, shortlist_assets):
+    """The multi-GPU shape of the service: one replica per device, batches dealt by one Batcher in one process.  Needs a
+    second GPU (skipped on a single-GPU box; exercised by tools/gpu_multi_r2.sh on the multi-GPU boxes)."""
+    try:
+        ctx1 = capi.Context(1)
+    except RuntimeError:
+        pytest.skip("needs two GPUs")
+    path, _ = tiny_model
+    sl_bin = open(shortlist_assets[0], "rb").read()
+    blob = open(path, "rb").read()
+    a, b = capi.Model(gpu_ctx, blob), capi.Model(ctx1, blob)
+    sents = synth.make_sentences(400, (2, 70), seed=321)
+    one, st1 = a.translate(sents, max_words=1024, shortlist_bin=sl_bin)
+    two, st2 = a.translate(sents, max_words=1024, shortlist_bin=sl_bin, replicas=[a, b])
+    assert st1["batches"] == st2["batches"] > 8
+    assert all(np.array_equal(x, y) for x, y in zip(one, two))
+    assert st2["target_tokens"] == st1["target_tokens"]
+    a.close(), b.close(), ctx1.close()
+
+
 def test_service_alignments_equal_oracle(gpu_ctx, tiny_model, shortlist_assets):
     """Response.alignments through the service call (Model.cc:84-108): per target token, head 0 of the last decoder
     layer's cross-attention over the sentence's own source tokens, for the tokens record() kept."""
