@@ -27,6 +27,7 @@ const char* last_error();
     cudaError_t _e = (expr);                                                               \
     if (_e != cudaSuccess) {                                                               \
       sb::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                   \
+      (void)cudaGetLastError(); /* reported: do not leave it for an unrelated later check */ \
       return 1;                                                                            \
     }                                                                                      \
   } while (0)
