@@ -104,6 +104,10 @@ int translate_multi(Model* const* models, size_t n_rep, slimt_b200_translate_io*
         set_error("translate: offsets must be non-decreasing");
         return 1;
       }
+      if (io->offsets[i + 1] == io->offsets[i]) {
+        set_error("translate: empty sentences are not valid input (every segment ends in EOS, TextProcessor.cc:132-143)");
+        return 1;
+      }
       batcher.enqueue(i, io->offsets[i + 1] - io->offsets[i]);
     }
     for (;;) {
@@ -118,10 +122,6 @@ int translate_multi(Model* const* models, size_t n_rep, slimt_b200_translate_io*
     if (p.width > static_cast<size_t>(m0.max_len())) {
       set_error("translate: a sentence of " + std::to_string(p.width) + " tokens exceeds the supported maximum of " +
                 std::to_string(m0.max_len()) + " (wrap longer input first: TextProcessor's wrap_length)");
-      return 1;
-    }
-    if (p.width == 0) {
-      set_error("translate: empty sentences are not valid input (every segment ends in EOS, TextProcessor.cc:132-143)");
       return 1;
     }
   }

@@ -243,3 +243,41 @@ def test_error_paths(gpu_ctx, tiny_model):
     out = m.forward(np.zeros((0, 4), np.uint32), np.zeros(0, np.uint32))
     assert out["steps"] == 0 and out["target_tokens"] == 0
     m.close()
+
+
+def test_malformed_model_images_are_reported_not_followed(gpu_ctx, tiny_model):
+    """io::load_items trusts nothing in the header here: counts, name / shape tables and blob sizes are checked against
+    what is left of the image (a truncated or garbage file is an error, as the reference's MmapFile / ABORT_IF paths)."""
+    import struct
+    path, _ = tiny_model
+    good = open(path, "rb").read()
+    for cut in (8, 24, 16 + 32 * 10, 16 + 32 * 193 + 100, 16 + 32 * 193 + 5000, len(good) // 2, len(good) - 300):
+        with pytest.raises(RuntimeError, match="truncated|too small|missing|unexpected|not a 2-D"):
+            capi.Model(gpu_ctx, good[:cut])
+    huge = bytearray(good)
+    struct.pack_into("<Q", huge, 8, 1 << 60)  # item count
+    with pytest.raises(RuntimeError, match="truncated"):
+        capi.Model(gpu_ctx, bytes(huge))
+    names = bytearray(good)
+    struct.pack_into("<Q", names, 16, 1 << 40)  # first item's name length
+    with pytest.raises(RuntimeError, match="truncated"):
+        capi.Model(gpu_ctx, bytes(names))
+    shape = bytearray(good)
+    struct.pack_into("<Q", shape, 16 + 16, 1 << 20)  # first item's rank
+    with pytest.raises(RuntimeError, match="truncated or malformed"):
+        capi.Model(gpu_ctx, bytes(shape))
+
+
+def test_translate_rejects_bad_requests_before_any_gpu_work(tiny_gpu, shortlist_assets):
+    m, _ = tiny_gpu
+    ok = synth.make_sentences(4, (3, 9), seed=1)
+    launches = m.ctx.launches()
+    with pytest.raises(RuntimeError, match="exceeds the supported maximum"):
+        m.translate(ok + [np.ones(300, np.uint32)], max_words=4096)
+    with pytest.raises(RuntimeError, match="empty sentences"):
+        m.translate(ok + [np.zeros(0, np.uint32)], max_words=4096)
+    assert m.ctx.launches() == launches, "a request that cannot be served must fail as a whole, before any batch runs"
+    bad_sl = bytearray(open(shortlist_assets[0], "rb").read())
+    bad_sl[-2] = 0xFF  # a target id far beyond the vocabulary
+    with pytest.raises(RuntimeError, match="out of bounds"):
+        m.translate([np.array([31999, 0], np.uint32)], max_words=64, shortlist_bin=bytes(bad_sl))
