@@ -27,6 +27,12 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 
+// phase stamp of consumer thread 0 into the CTA's trace slots (groups 0..5 of the CTA; no-op without a trace buffer)
+#define RC_TRACE(slot)                                                                         \
+  do {                                                                                         \
+    if (a.trace && ct == 0 && it < 6) a.trace[blockIdx.x * 128 + 8 + 16 * it + (slot)] = clock64(); \
+  } while (0)
+
 namespace sb {
 
 namespace {
@@ -43,8 +49,9 @@ struct Smem {
   static constexpr int wv = wk + 64 * 1024;
   static constexpr int ak = wv + 64 * 1024;           // 2 k-blocks x [128 key rows x 128 B]
   static constexpr int av = ak + 32 * 1024;
-  static constexpr int qs = av + 32 * 1024;           // f32 [4][256]
-  static constexpr int ps = qs + kGroup * kE * 4;     // f32 [4][8][32]
+  static constexpr int qs = av + 32 * 1024;           // f32 [2 buffers][4][256]: the group's query rows, filled by cp.async
+  static constexpr int lens = qs + 2 * kGroup * kE * 4;  // i32 [2 buffers][4]: the group's sentence lengths
+  static constexpr int ps = lens + 2 * kGroup * 4;    // f32 [4][8][32]
   static constexpr int pbk = ps + kGroup * kH * kKeys * 4;  // f32 [256]
   static constexpr int pmax = pbk + kE * 4;           // f32 [4 key blocks][8 heads]: per-block score maxima (KB > 1)
   static constexpr int psum = pmax + kGroup * kH * 4;     // f32 [4 key blocks][8 heads]: per-block sums (tolerance mode, KB > 1)
@@ -70,7 +77,8 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
   uint8_t* s_wv = smem + Smem::wv;
   uint8_t* s_ak = smem + Smem::ak;
   uint8_t* s_av = smem + Smem::av;
-  float* s_q = reinterpret_cast<float*>(smem + Smem::qs);
+  float* s_q_all = reinterpret_cast<float*>(smem + Smem::qs);
+  int* s_len_all = reinterpret_cast<int*>(smem + Smem::lens);
   float* s_p = reinterpret_cast<float*>(smem + Smem::ps);
   float* s_pbk = reinterpret_cast<float*>(smem + Smem::pbk);
   float* s_pmax = reinterpret_cast<float*>(smem + Smem::pmax);
@@ -208,56 +216,77 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
     const int v_feat = v_mb * 128 + qd * 32 + lane;
     const int v_head = v_mb * 4 + qd;
     const float pbv = a.pb_v[v_feat];
-    // Global inputs of a group (its query rows and sentence lengths) are fetched one group ahead into registers, so
-    // their latency hides behind the previous group's arithmetic instead of opening every iteration.
+    // Global inputs of a group (its query rows and sentence lengths) are fetched one group ahead with cp.async straight
+    // into the other half of a double-buffered shared block: their latency hides behind the previous group's arithmetic
+    // and they occupy no registers meanwhile (held in registers they pushed the kernel over its 96-register budget: the
+    // compiler then spilled the freshly loaded values, i.e. waited for the loads it had just issued).
     constexpr int kQPer = NS * kE / kConsThreads;  // query floats per consumer thread: 2 (KB = 1) or 1 (KB = 2)
     static_assert(NS * kE == kQPer * kConsThreads, "query floats per consumer thread");
     const int kj = qd / KB;             // K phase: this warp's sentence of the group ...
     const int kblk = qd % KB;           // ... and which of its key blocks sits in the warp's lane quadrant
     const int key = kblk * kKeys + lane;
     const int vj0 = KB == 1 ? (sub >> 1) * 2 : (sub >> 1);  // V phase: first (KB = 1: of two) sentence of this warp
-    float q_nx[kQPer];
-    int len_nx[3];  // K phase: sentence kj; V phase: sentences vj0 (and vj0 + 1 when KB = 1)
-    auto fetch_group = [&](int g) {
-      const int b0 = g * NS;
+    // A group's NS query rows are contiguous: float i of the group is a.q[g * NS * kE + i], valid while below B * kE.
+    const int q_end = a.B * kE;
+    const uint32_t sq_u32 = smem_u32(s_q_all), slen_u32 = smem_u32(s_len_all);
+    auto fetch_group = [&](int g, uint32_t buf) {
+      const int q0 = g * (NS * kE) + ct;
 #pragma unroll
       for (int r = 0; r < kQPer; r++) {
-        const int i = ct + r * kConsThreads;
-        const int b = b0 + i / kE;
-        q_nx[r] = (g < n_groups && b < a.B) ? __ldg(a.q + static_cast<size_t>(b) * kE + (i % kE)) : 0.0f;
+        const int i = q0 + r * kConsThreads;
+        cp_async4(sq_u32 + (buf * kGroup * kE + ct + r * kConsThreads) * 4, a.q + (i < q_end ? i : 0), i < q_end);
       }
-      const int js[3] = {kj, vj0, vj0 + 1};
-#pragma unroll
-      for (int r = 0; r < 3; r++) {
-        const int b = b0 + js[r];
-        len_nx[r] = (g < n_groups && js[r] < NS && b < a.B) ? min(static_cast<int>(__ldg(a.lengths + b)), a.T) : 0;
+      if (ct < NS) {
+        const int b = g * NS + ct;
+        cp_async4(slen_u32 + (buf * kGroup + ct) * 4, a.lengths + (b < a.B ? b : 0), b < a.B);
       }
+      cp_async_commit();
     };
-    fetch_group(blockIdx.x);
+    if (a.trace && ct == 0) a.trace[blockIdx.x * 128] = clock64();
+    fetch_group(blockIdx.x, 0);
+    // Accumulators travel TMEM -> registers one phase ahead of their use: the V accumulators are requested as soon as the
+    // scores are formed (the K registers are dead then) and arrive during the softmax; the next group's K accumulators are
+    // requested at the end of the V phase and arrive during the loop head.  tmem_ld_wait_dep() is the only point after
+    // which the registers may be read.
+    uint32_t v0[32], v1[32];
+    const int h0 = sub * 2;
+    const int c0 = (sub >> 1) * 64;  // V phase: the warp's 64 key columns of the group
+    auto request_k = [&](uint32_t ph) {
+      mbar_wait(k_done, ph);
+      tc_fence_after();
+      tmem_ld32_nowait(tmem_k + lane_sel + h0 * 32, v0);
+      tmem_ld32_nowait(tmem_k + lane_sel + h0 * 32 + 32, v1);
+    };
+    auto request_v = [&](uint32_t ph) {
+      mbar_wait(v_done, ph);
+      tc_fence_after();
+      tmem_ld32_nowait(tmem_v + lane_sel + v_mb * 128 + c0, v0);
+      tmem_ld32_nowait(tmem_v + lane_sel + v_mb * 128 + c0 + 32, v1);
+    };
+    if (static_cast<int>(blockIdx.x) < n_groups) request_k(0);
     uint32_t it = 0;
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x, it++) {
       const uint32_t ph = it & 1;
       const int b0 = g * NS;
-      // the group's query rows (s_q is free: the previous group's K phase ended before its mid-group barrier)
-#pragma unroll
-      for (int r = 0; r < kQPer; r++) s_q[ct + r * kConsThreads] = q_nx[r];
-      const int len_k = len_nx[0];
-      const int len_v[2] = {len_nx[1], len_nx[2]};
-      fetch_group(g + gridDim.x);
+      // this group's rows and lengths were requested a group ago; the other buffer is free (its readers, the previous
+      // group's K and V phases, are behind this warp) and takes the next group's
+      const float* s_q = s_q_all + (it & 1) * kGroup * kE;
+      const int* s_len = s_len_all + (it & 1) * kGroup;
+      cp_async_wait_all();
+      fetch_group(g + gridDim.x, (it & 1) ^ 1);
+      RC_TRACE(0);
       named_bar_sync(1, kConsThreads);
+      RC_TRACE(1);
 
       // ---- K phase: quadrant = 32 keys of a sentence, lane = key, two heads per warp
       {
         const int j = kj;
         const int b = b0 + j;
+        const int len_k = min(s_len[kj], a.T);
         const bool valid = key < len_k;
-        mbar_wait(k_done, ph);
-        tc_fence_after();
-        uint32_t v0[32], v1[32];
-        const int h0 = sub * 2;
-        tmem_ld32_nowait(tmem_k + lane_sel + h0 * 32, v0);
-        tmem_ld32_nowait(tmem_k + lane_sel + h0 * 32 + 32, v1);
-        tmem_ld_wait();
+        RC_TRACE(2);
+        tmem_ld_wait_dep(v0, v1);
+        RC_TRACE(3);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(k_drained);
@@ -286,6 +315,7 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
             sc[0] = valid ? acc0 * sk : -3.402823466e+38f;
             sc[1] = valid ? acc1 * sk : -3.402823466e+38f;
           }
+          request_v(ph);
           float mx[2] = {sc[0], sc[1]};
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
@@ -349,6 +379,8 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
           sc[0] = __fmul_rn(a.dk, acc0);
           sc[1] = __fmul_rn(a.dk, acc1);
         }
+        RC_TRACE(4);
+        request_v(ph);
         // softmax over the sentence's keys (slimt/TensorOps.cc:282-315): max, exp, sum in key order, divide.  Both
         // heads advance together: nothing is stored between the two expf evaluations (a store would pin the second
         // one's table load behind it), so their double-precision chains interleave.
@@ -402,24 +434,25 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
         }
         }  // exact K phase
       }
+      RC_TRACE(5);
       named_bar_sync(1, kConsThreads);
+      RC_TRACE(6);
 
       // ---- V phase: lane = output feature; KB = 1: two sentences per warp, KB = 2: one sentence of up to 64 keys
       {
-        mbar_wait(v_done, ph);
-        tc_fence_after();
-        uint32_t v0[32], v1[32];
-        const int c0 = (sub >> 1) * 64;  // the warp's 64 key columns of the group
-        tmem_ld32_nowait(tmem_v + lane_sel + v_mb * 128 + c0, v0);
-        tmem_ld32_nowait(tmem_v + lane_sel + v_mb * 128 + c0 + 32, v1);
-        tmem_ld_wait();
+        RC_TRACE(7);
+        tmem_ld_wait_dep(v0, v1);
+        RC_TRACE(8);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(v_drained);
         auto emit = [&](int b, float acc) {
           const size_t off = static_cast<size_t>(b) * kE + v_feat;
           if (a.out_f32) a.out_f32[off] = acc;
-          for (int k = 0; k < a.qo.n; k++) a.qo.ptr[k][off] = static_cast<int8_t>(quantize<kFast>(acc, a.qo.aq[k]));
+          // the usual case is one consumer (Wo): constant indices keep its multiplier and pointer in the constant bank
+          if (a.qo.n == 1) a.qo.ptr[0][off] = static_cast<int8_t>(quantize<kFast>(acc, a.qo.aq[0]));
+          else
+            for (int k = 0; k < a.qo.n; k++) a.qo.ptr[k][off] = static_cast<int8_t>(quantize<kFast>(acc, a.qo.aq[k]));
         };
         constexpr int kRow = KB * kKeys;
         if constexpr (kFast) {
@@ -466,6 +499,7 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
         } else
         if constexpr (KB == 1) {
           const int j0 = vj0;
+          const int len_v[2] = {min(s_len[j0], a.T), min(s_len[j0 + 1], a.T)};
           if (len_v[0] == kKeys && len_v[1] == kKeys && b0 + j0 + 1 < a.B) {
             // both sentences full: their two chains advance together
             const float* pr0 = s_p + (j0 * kH + v_head) * kKeys;
@@ -484,8 +518,10 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
               acc0 = fmaf(p0.w, dequant1(static_cast<int>(v0[l + 3]), a.um_v, pbv), acc0);
               acc1 = fmaf(p1.w, dequant1(static_cast<int>(v1[l + 3]), a.um_v, pbv), acc1);
             }
+            RC_TRACE(9);
             emit(b0 + j0, acc0);
             emit(b0 + j0 + 1, acc1);
+            RC_TRACE(10);
           } else {
 #pragma unroll
             for (int jj = 0; jj < 2; jj++) {
@@ -509,7 +545,7 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
           const int j = vj0;
           const int b = b0 + j;
           if (b < a.B) {
-            const int len = len_v[0];
+            const int len = min(s_len[j], a.T);
             const float* pr = s_p + (j * kH + v_head) * kRow;
             float acc = 0.0f;
             if (len == kRow) {
@@ -543,6 +579,7 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
           }
         }
       }
+      if (g + static_cast<int>(gridDim.x) < n_groups) request_k(ph ^ 1);  // the next group's K accumulators, see above
     }
   }
   tc_fence_before();

@@ -747,8 +747,8 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
   long long* trace_buf = nullptr;
   const size_t trace_n = static_cast<size_t>(c.num_sms) * kTraceSlots;
   if (trace_path) {
-    SB_CUDA(cudaMallocManaged(&trace_buf, 3 * trace_n * sizeof(long long)));
-    SB_CUDA(cudaMemsetAsync(trace_buf, 0, 3 * trace_n * sizeof(long long), s));
+    SB_CUDA(cudaMallocManaged(&trace_buf, 4 * trace_n * sizeof(long long)));
+    SB_CUDA(cudaMemsetAsync(trace_buf, 0, 4 * trace_n * sizeof(long long), s));
   }
 
   // ---- embedding (Model.cc:195-197)
@@ -1075,6 +1075,7 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
         k.qo = qouts();
         qadd(k.qo, caq, L.ctx.o.aq);
         k.attn_head0 = last ? d_align : nullptr;
+        if (trace_buf && step == 3 && l == 0) k.trace = trace_buf + 3 * trace_n;
         const double Bd = B, Ed = E;
         LaunchScope ls(c, "dec_cross_attention_rc", 2.0 * Bd * (T > 32 ? 64.0 : 32.0) * Ed * 2.0 * Ed,
                        2.0 * src_tokens * Ed + 2.0 * Ed * Ed + 5.0 * Bd * Ed);  // valid keys only
@@ -1186,11 +1187,11 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
   if (trace_buf) {
     SB_CUDA(cudaStreamSynchronize(s));
     if (FILE* f = fopen(trace_path, "w")) {
-      for (int k = 0; k < 3; k++)
+      for (int k = 0; k < 4; k++)
         for (int cta = 0; cta < c.num_sms; cta++) {
           const long long* t = trace_buf + k * trace_n + static_cast<size_t>(cta) * kTraceSlots;
           if (t[0] == 0) continue;
-          fprintf(f, "%s %d", k == 0 ? "ssru" : k == 1 ? "ffn" : "encffn", cta);
+          fprintf(f, "%s %d", k == 0 ? "ssru" : k == 1 ? "ffn" : k == 2 ? "encffn" : "cross", cta);
           for (int i = 0; i < kTraceSlots; i++) fprintf(f, " %lld", t[i] ? t[i] - t[0] : -1);
           fprintf(f, "\n");
         }

@@ -81,6 +81,12 @@ template <uint32_t kCols>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
 }
+// 4-byte asynchronous global -> shared copy (no register holds the value in flight); !valid zero-fills the word
+__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_smem), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -145,6 +151,13 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8]
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The same wait for loads issued far ahead of their use: every register of the two destination arrays is made an
+// output of a statement ordered after the wait, so that no read (or copy) of them can be scheduled before it.
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v0)[32], uint32_t (&v1)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; i++) asm volatile("" : "+r"(v0[i]), "+r"(v1[i]));
+}
 
 // registers -> TMEM (same shape).
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {

@@ -30,6 +30,12 @@ for i, nm in enumerate(FINE):
 SSRU = {0: "start", 1: "setup done", 2: "mma: x landed", 3: "mma: Wf,W issued", 14: "epi: state/x rows loaded", 4: "epi: Wf,W done",
         5: "epi: x parked", 6: "epi: LN stats", 7: "epi: h operand ready", 8: "mma: h seen", 9: "mma: Wq issued", 10: "epi: Wq done",
         11: "epi: q written", 13: "exit"}
+CROSS = {0: "start"}
+RC = ["group: q stored", "after group barrier", "K accumulators ready", "K in registers", "scores formed", "softmax done",
+      "after mid barrier", "V accumulators ready", "V in registers", "V sums formed", "V emitted"]
+for it in range(6):
+    for i, nm in enumerate(RC):
+        CROSS[8 + 16 * it + i] = f"group {it}: {nm}"
 
 
 def main():
@@ -51,12 +57,12 @@ def main():
             os.environ["SLIMT_B200_TRACE"] = raw
         model.forward(tok, lens, shortlist=sl)
     os.environ.pop("SLIMT_B200_TRACE")
-    rows = {"ssru": [], "ffn": [], "encffn": []}
+    rows = {"ssru": [], "ffn": [], "encffn": [], "cross": []}
     for line in open(raw):
         p = line.split()
         rows[p[0]].append([int(x) for x in p[2:]])
     with open(out_path, "w") as f:
-        for name, names in (("ssru", SSRU), ("ffn", FFN), ("encffn", FFN)):
+        for name, names in (("ssru", SSRU), ("ffn", FFN), ("encffn", FFN), ("cross", CROSS)):
             if not rows[name]:
                 continue
             a = np.array(rows[name], dtype=np.float64)
