@@ -19,11 +19,14 @@
 // Macros.hh:30-42) and throws std::runtime_error from its loaders (Io.cc:294-309); here every failure of the
 // C ABI is a std::runtime_error carrying slimt_b200_last_error().  There is no CPU fallback.
 #pragma once
+#include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <future>
 #include <memory>
 #include <mutex>
@@ -289,7 +292,7 @@ class Model {
       : Model(config, map_files(package), std::move(devices), 0) {}
 
   Model(const Config &config, const Package<View> &package, std::vector<int> devices = {0})
-      : config_(config), devices_(std::move(devices)) {
+      : id_(next_id()), config_(config), devices_(std::move(devices)) {
     create(package);
   }
   ~Model() {
@@ -307,8 +310,12 @@ class Model {
     if (!p.shortlist.empty()) m.shortlist = io::MmapFile(p.shortlist);
     return m;
   }
+  static size_t next_id() {  // Model.cc:28, 53: every model of the process gets the next id (the cache key's seed)
+    static std::atomic<size_t> model_id{0};
+    return model_id++;
+  }
   Model(const Config &config, Mmap &&files, std::vector<int> devices, int /*tag*/)
-      : config_(config), devices_(std::move(devices)), mmap_(std::move(files)) {
+      : id_(next_id()), config_(config), devices_(std::move(devices)), mmap_(std::move(files)) {
     create(Package<View>{{mmap_.model.data(), mmap_.model.size()},
                          {mmap_.vocabulary.data(), mmap_.vocabulary.size()},
                          {mmap_.shortlist.data(), mmap_.shortlist.size()}});
@@ -375,6 +382,7 @@ class Model {
     return histories;
   }
   const Config &config() const { return config_; }
+  size_t id() const { return id_; }  // Model.hh:62
   size_t vocabulary_size() const { return vocab_; }
   const std::vector<int> &devices() const { return devices_; }
   slimt_b200_model *handle() const { return replicas_[0]; }
@@ -382,6 +390,7 @@ class Model {
   const std::vector<char> &shortlist_image() const { return shortlist_; }
 
  private:
+  size_t id_;
   Config config_;
   std::vector<int> devices_;
   Mmap mmap_;  // only used by the path constructor
@@ -396,6 +405,69 @@ inline Model::Config tiny() { return Model::Config{6, 2, 2, 8, "sentence"}; }
 inline Model::Config base() { return Model::Config{6, 2, 2, 8, "sentence"}; }
 inline Model::Config nano() { return Model::Config{4, 2, 2, 8, "sentence"}; }
 }  // namespace preset
+
+// ---------------------------------------------------------------- translation cache (slimt/Cache.hh, Request.cc:20-26)
+// AtomicCache (Cache.hh:11-58): a direct-mapped table -- no probing, a newer key simply replaces the record in its
+// slot -- with one mutex per bucket of slots.  The key of a translation is cache_key(model id, segment words), the
+// value its History; two segments whose keys collide are indistinguishable, as in the reference.
+template <class Key, class Value, class Hash = std::hash<Key>, class Equals = std::equal_to<Key>>
+class AtomicCache {
+ public:
+  explicit AtomicCache(size_t size, size_t buckets) : records_(size), locks_(buckets) {}
+  std::pair<bool, Value> find(const Key &key) const {
+    const size_t index = hash_(key) % records_.size();
+    std::lock_guard<std::mutex> guard(locks_[index % locks_.size()]);
+    const Record &candidate = records_[index];
+    if (equals_(key, candidate.first)) return {true, candidate.second};
+    return {false, Value()};
+  }
+  void store(const Key &key, Value value) {
+    const size_t index = hash_(key) % records_.size();
+    std::lock_guard<std::mutex> guard(locks_[index % locks_.size()]);
+    records_[index] = Record(key, std::move(value));
+  }
+
+ private:
+  using Record = std::pair<Key, Value>;
+  std::vector<Record> records_;
+  mutable std::vector<std::mutex> locks_;
+  Hash hash_;
+  Equals equals_;
+};
+using TranslationCache = AtomicCache<size_t, History>;  // Types.hh:62
+
+// Utils.hh:47-57 (boost-style combinator over std::hash) and Request.cc:20-26
+template <class T, class HashType = std::size_t>
+inline void hash_combine(HashType &seed, const T &v) {
+  seed ^= (static_cast<HashType>(std::hash<T>()(v)) + 0x9e3779b9 + (seed << 6) + (seed >> 2));
+}
+inline size_t cache_key(size_t model_id, const Words &words) {
+  size_t seed = model_id;
+  for (size_t word : words) hash_combine<size_t>(seed, word);
+  return seed;
+}
+inline Ptr<TranslationCache> make_cache(size_t cache_size) {  // Frontend.cc:78-85
+  constexpr size_t kCacheBucketSize = 16;
+  return cache_size > 0 ? std::make_shared<TranslationCache>(cache_size, kCacheBucketSize) : nullptr;
+}
+
+// TextProcessor::wrap (TextProcessor.cc:123-157) on word ids: a sentence of more than wrap_length tokens is cut into
+// segments of wrap_length - 1 words, each closed with its own EOS (the decoder needs the marker); shorter sentences
+// pass through untouched.  The sentence's own closing EOS, when present, is not counted as a word.
+inline void wrap(const Words &sentence, size_t wrap_length, Word eos_id, Sentences &segments) {
+  if (sentence.empty()) return;  // TextProcessor.cc:113-117: nothing to translate, no segment
+  if (wrap_length < 2 || sentence.size() <= wrap_length) {
+    segments.push_back(sentence);
+    return;
+  }
+  const size_t words = sentence.back() == eos_id ? sentence.size() - 1 : sentence.size();
+  const size_t step = wrap_length - 1;
+  for (size_t offset = 0; offset < words; offset += step) {
+    const size_t diff = std::min(step, words - offset);
+    segments.emplace_back(sentence.begin() + offset, sentence.begin() + offset + diff);
+    segments.back().push_back(eos_id);
+  }
+}
 
 // ---------------------------------------------------------------- services (slimt/Frontend.hh, slimt/Response.hh)
 struct Config {
@@ -416,9 +488,12 @@ struct Options {
 // the sentences' word ids; alignments[i][t][s] = p(source token s | target token t) of sentence i (head 0 of the last
 // decoder layer's cross-attention, Model.cc:84-108), empty unless Options::alignment.
 struct Response {
-  Sentences source;
+  Sentences source;  // one entry per SEGMENT (a sentence longer than Config::wrap_length is several, TextProcessor.cc:123)
   Sentences target;
   std::vector<Alignment> alignments;
+  // segments [sentence_begin[i], sentence_begin[i + 1]) came from input sentence i (the reference keeps this relation
+  // in the byte ranges of its AnnotatedText); the identity while nothing was wrapped
+  std::vector<size_t> sentence_begin;
   size_t size() const { return source.size(); }
 };
 
@@ -427,7 +502,8 @@ struct Response {
 // what remains is the marginalisation p(s | t) = sum_q p(s | q) p(q | t).
 inline Response combine(Response &&first, Response &&second) {
   Response out;
-  if (!first.alignments.empty() && !second.alignments.empty()) {
+  // (a pivot sentence the second service had to wrap again has no one-to-one segment any more: no combined alignment)
+  if (!first.alignments.empty() && second.alignments.size() == first.alignments.size()) {
     for (size_t i = 0; i < first.source.size(); i++) {
       const Alignment &s_given_q = first.alignments[i];
       const Alignment &q_given_t = second.alignments[i];
@@ -441,6 +517,7 @@ inline Response combine(Response &&first, Response &&second) {
   }
   out.source = std::move(first.source);
   out.target = std::move(second.target);
+  out.sentence_begin = std::move(first.sentence_begin);
   return out;
 }
 
@@ -448,24 +525,67 @@ inline Response combine(Response &&first, Response &&second) {
 // Model::forward per batch -- dealt to every replica of the model -- all inside one C-ABI call.
 class Blocking {
  public:
-  explicit Blocking(const Config &config) : config_(config) {}
+  explicit Blocking(const Config &config) : config_(config), cache_(make_cache(config.cache_size)) {}
+  // a service that shares another one's cache (Async's workers, Frontend.cc:207-210)
+  Blocking(const Config &config, Ptr<TranslationCache> cache) : config_(config), cache_(std::move(cache)) {}
+
   Response translate(const Ptr<Model> &model, const Sentences &sources, const Options &options = Options()) {
+    Response response;
+    // segments (TextProcessor::process + wrap, on word ids)
+    response.sentence_begin.push_back(0);
+    for (const Words &s : sources) {
+      wrap(s, config_.wrap_length, model->config().eos_id, response.source);
+      response.sentence_begin.push_back(response.source.size());
+    }
+    const Sentences &segments = response.source;
+    // cache prefill (Request.cc:58-78): a segment this model has translated before is not batched again.  A record
+    // stored by a request that did not ask for alignments cannot answer one that does.
+    Histories histories(segments.size());
+    std::vector<size_t> todo;
+    for (size_t i = 0; i < segments.size(); i++) {
+      if (cache_) {
+        auto [found, history] = cache_->find(cache_key(model->id(), segments[i]));
+        if (found && history && (!options.alignment || history->alignment.size() == history->target.size())) {
+          histories[i] = history;
+          cache_hits_++;
+          continue;
+        }
+      }
+      todo.push_back(i);
+    }
+    if (!todo.empty()) run(model, segments, todo, options, histories);
+    for (size_t i : todo)
+      if (cache_) cache_->store(cache_key(model->id(), segments[i]), histories[i]);  // Request.cc:120-125
+    response.target.reserve(segments.size());
+    for (const History &h : histories) response.target.push_back(h->target);
+    if (options.alignment)
+      for (const History &h : histories) response.alignments.push_back(h->alignment);
+    return response;
+  }
+  size_t cache_hits() const { return cache_hits_; }
+
+ private:
+  // Frontend.cc:91-145 + exhaust() :42-60 for the segments listed in `todo`: one Batcher, per-batch shortlist,
+  // Model::forward per batch -- dealt to every replica of the model -- all inside one C-ABI call.
+  void run(const Ptr<Model> &model, const Sentences &segments, const std::vector<size_t> &todo, const Options &options,
+           Histories &histories) {
     std::vector<uint32_t> tokens;
     std::vector<uint64_t> offsets(1, 0);
     size_t longest = 0;
-    for (const Words &s : sources) {
+    for (size_t i : todo) {
+      const Words &s = segments[i];
       tokens.insert(tokens.end(), s.begin(), s.end());
       offsets.push_back(tokens.size());
       longest = std::max(longest, s.size());
     }
     const size_t per = std::max<size_t>(1, static_cast<size_t>(config_.tgt_length_limit_factor * static_cast<float>(longest)));
-    std::vector<uint32_t> out(std::max<size_t>(1, per * sources.size()));
-    std::vector<uint64_t> out_offsets(sources.size() + 1, 0);
+    std::vector<uint32_t> out(std::max<size_t>(1, per * todo.size()));
+    std::vector<uint64_t> out_offsets(todo.size() + 1, 0);
     std::vector<float> align;
-    std::vector<uint64_t> align_offsets(sources.size() + 1, 0);
+    std::vector<uint64_t> align_offsets(todo.size() + 1, 0);
     slimt_b200_translate_io io;
     std::memset(&io, 0, sizeof(io));
-    io.tokens = tokens.data(), io.offsets = offsets.data(), io.n_sentences = sources.size();
+    io.tokens = tokens.data(), io.offsets = offsets.data(), io.n_sentences = todo.size();
     io.max_words = config_.max_words, io.limit_factor = config_.tgt_length_limit_factor;
     const std::vector<char> &sl = model->shortlist_image();
     io.shortlist_bin = sl.empty() ? nullptr : sl.data(), io.shortlist_bytes = sl.size();
@@ -476,21 +596,19 @@ class Blocking {
     }
     const std::vector<slimt_b200_model *> &replicas = model->replicas();
     detail::check(slimt_b200_translate_multi(replicas.data(), replicas.size(), &io), "slimt_b200_translate_multi");
-    Response response;
-    response.source = sources;
-    response.target.resize(sources.size());
-    for (size_t i = 0; i < sources.size(); i++)
-      response.target[i].assign(out.begin() + out_offsets[i], out.begin() + out_offsets[i + 1]);
-    if (options.alignment) {
-      response.alignments.resize(sources.size());
-      for (size_t i = 0; i < sources.size(); i++) {
-        const size_t S = sources[i].size();
-        const float *p = align.data() + align_offsets[i];
-        for (size_t t = 0; t < response.target[i].size(); t++) response.alignments[i].emplace_back(p + t * S, p + (t + 1) * S);
+    for (size_t k = 0; k < todo.size(); k++) {
+      auto h = std::make_shared<Hypothesis>();
+      h->target.assign(out.begin() + out_offsets[k], out.begin() + out_offsets[k + 1]);
+      if (options.alignment) {
+        const size_t S = segments[todo[k]].size();
+        const float *p = align.data() + align_offsets[k];
+        for (size_t t = 0; t < h->target.size(); t++) h->alignment.emplace_back(p + t * S, p + (t + 1) * S);
       }
+      histories[todo[k]] = std::move(h);
     }
-    return response;
   }
+
+ public:
   // Blocking::pivot (Frontend.cc:147-205) on word ids: source -> pivot with `first`, pivot -> target with `second`.
   // The reference detokenises the pivot text and re-tokenises it with the second model's TextProcessor (text
   // handling: out of scope here), so at this level the two models must share the pivot-language vocabulary; the
@@ -504,6 +622,8 @@ class Blocking {
 
  private:
   Config config_;
+  Ptr<TranslationCache> cache_;
+  size_t cache_hits_ = 0;
 };
 
 // Async (Frontend.cc:207-323): `workers` threads take requests from one queue and answer through futures.  A request
@@ -511,7 +631,7 @@ class Blocking {
 // the same time share the replicas (each device context serialises the batches it is given).
 class Async {
  public:
-  explicit Async(const Config &config) : config_(config) {
+  explicit Async(const Config &config) : config_(config), cache_(make_cache(config.cache_size)) {
     for (size_t i = 0; i < std::max<size_t>(1, config_.workers); i++) workers_.emplace_back([this]() { work(); });
   }
   ~Async() {
@@ -548,7 +668,7 @@ class Async {
     return f;
   }
   void work() {
-    Blocking service(config_);
+    Blocking service(config_, cache_);  // one cache for the whole service (Frontend.cc:207-210)
     for (;;) {
       Job job;
       {
@@ -567,6 +687,7 @@ class Async {
     }
   }
   Config config_;
+  Ptr<TranslationCache> cache_;
   std::vector<std::thread> workers_;
   std::deque<Job> queue_;
   std::mutex mu_;

@@ -885,7 +885,10 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
   // ---- cross-attention K/V.  The reference re-projects them every step (Modules.cc:244-249); so does the
   // recompute kernel (tensor cores, from the u8 encoder output); otherwise they are projected once and cached.
   const char* ca_env = getenv("SLIMT_B200_CROSS");
-  const bool cross_rc = cross_attention_rc_supported(E, H, dh, T) && !(ca_env && strcmp(ca_env, "cached") == 0);
+  const bool ca_cached = ca_env && strcmp(ca_env, "cached") == 0;
+  // long sentences (65 .. 256 tokens) take the sentence-at-a-time recompute kernel (cross_attention_rcl.cu; bit-exact mode)
+  const bool cross_rcl = !ca_cached && !c.fast && !cross_attention_rc_supported(E, H, dh, T) && cross_attention_rcl_supported(E, H, dh, T);
+  const bool cross_rc = cross_rcl || (cross_attention_rc_supported(E, H, dh, T) && !ca_cached);
   std::vector<CUtensorMap> mapAk(Ld), mapAv(Ld);
   if (cross_rc) {
     for (int l = 0; l < Ld; l++)
@@ -1077,9 +1080,9 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
         k.attn_head0 = last ? d_align : nullptr;
         if (trace_buf && step == 3 && l == 0) k.trace = trace_buf + 3 * trace_n;
         const double Bd = B, Ed = E;
-        LaunchScope ls(c, "dec_cross_attention_rc", 2.0 * Bd * (T > 32 ? 64.0 : 32.0) * Ed * 2.0 * Ed,
+        LaunchScope ls(c, "dec_cross_attention_rc", 2.0 * (cross_rcl ? src_tokens : Bd * (T > 32 ? 64.0 : 32.0)) * Ed * 2.0 * Ed,
                        2.0 * src_tokens * Ed + 2.0 * Ed * Ed + 5.0 * Bd * Ed);  // valid keys only
-        if (launch_cross_attention_rc(k, c.num_sms, c.fast, s)) {
+        if (cross_rcl ? launch_cross_attention_rcl(k, c.num_sms, s) : launch_cross_attention_rc(k, c.num_sms, c.fast, s)) {
           set_error("recompute cross-attention launch failed");
           return 1;
         }

@@ -125,6 +125,46 @@ int main(int argc, char **argv) {
       }
       if (f4.get().target != plain.target) throw std::runtime_error("concurrent request on a shared device context differs");
     }
+    // 5. wrap_length and the translation cache (TextProcessor.cc:123-157, Cache.hh, Request.cc:58-78, 120-125)
+    {
+      slimt::Config wrapped = config;
+      wrapped.workers = 1;
+      wrapped.wrap_length = 6;
+      slimt::Blocking service(wrapped);
+      slimt::Response first = service.translate(model, sources, with_alignment);
+      if (first.sentence_begin.size() != sources.size() + 1 || first.sentence_begin.back() != first.source.size())
+        throw std::runtime_error("wrap: sentence map");
+      if (first.source.size() <= sources.size()) throw std::runtime_error("wrap: nothing was wrapped");
+      for (size_t i = 0; i < sources.size(); i++) {
+        slimt::Words joined;
+        for (size_t k = first.sentence_begin[i]; k < first.sentence_begin[i + 1]; k++) {
+          const slimt::Words &seg = first.source[k];
+          if (seg.size() > wrapped.wrap_length || seg.back() != 0) throw std::runtime_error("wrap: segment shape");
+          const bool last = k + 1 == first.sentence_begin[i + 1];
+          joined.insert(joined.end(), seg.begin(), seg.end() - ((last && sources[i].back() == 0) || !last ? 1 : 0));
+          if (last && sources[i].back() == 0) joined.push_back(0);
+        }
+        if (sources[i].size() > wrapped.wrap_length && joined != sources[i]) throw std::runtime_error("wrap: words lost");
+      }
+      if (service.cache_hits() != 0) throw std::runtime_error("cache: hit on first sight");
+      // the same request again: every segment comes from the cache, identical histories
+      slimt::Response again = service.translate(model, sources, with_alignment);
+      if (service.cache_hits() != first.source.size()) throw std::runtime_error("cache: expected every segment to hit");
+      if (again.target != first.target || again.alignments != first.alignments) throw std::runtime_error("cache: different answer");
+      // the segments translated directly by a service without a cache (same batches as the first pass)
+      slimt::Config plain_config = wrapped;
+      plain_config.cache_size = 0;
+      slimt::Blocking no_cache(plain_config);
+      slimt::Response direct = no_cache.translate(model, first.source, with_alignment);
+      if (direct.target != first.target || direct.alignments != first.alignments) throw std::runtime_error("wrap: segments differ");
+      if (no_cache.cache_hits() != 0) throw std::runtime_error("cache: disabled cache hit");
+      // another model does not see this model's records
+      auto other = std::make_shared<slimt::Model>(slimt::preset::tiny(), paths);
+      if (other->id() == model->id()) throw std::runtime_error("model ids");
+      const size_t before = service.cache_hits();
+      slimt::Response other_response = service.translate(other, sources, with_alignment);
+      if (service.cache_hits() != before || other_response.target != first.target) throw std::runtime_error("cache: model id not in the key");
+    }
     std::printf("host_api_test ok\n");
     return 0;
   } catch (const std::exception &e) {

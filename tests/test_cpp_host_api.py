@@ -54,6 +54,41 @@ def test_host_layer_builds_and_refuses_to_run_without_gpu(tiny_model, tmp_path):
     assert "no CPU fallback" in r.stderr or "CUDA" in r.stderr
 
 
+LOGIC = os.path.join(ROOT, "tests", "cpp", "host_logic_test")
+
+
+def _wrap_ref(words, wrap_length, eos=0):
+    """TextProcessor::wrap (slimt/TextProcessor.cc:123-157): segments of wrap_length - 1 words, each with its own EOS."""
+    step = wrap_length - 1
+    return [words[o:o + step] + [eos] for o in range(0, len(words), step)]
+
+
+def _cache_key_ref(model_id, words):
+    """cache_key (slimt/Request.cc:20-26) over hash_combine (Utils.hh:47-57); std::hash<size_t> is the identity."""
+    mask = (1 << 64) - 1
+    seed = model_id
+    for w in words:
+        seed ^= (w + 0x9e3779b9 + ((seed << 6) & mask) + (seed >> 2)) & mask
+    return seed
+
+
+@pytest.mark.parametrize("length,wrap_length", [(12, 6), (5, 6), (6, 6), (1, 2), (300, 128), (255, 128), (10, 1)])
+def test_host_wrap_and_cache_key(length, wrap_length):
+    """CPU-only pieces of the C++ host layer: wrapping of long sentences on word ids, the cache key, AtomicCache."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "slimt_b200", "csrc"), "host_logic"])
+    out = subprocess.run([LOGIC, str(length), str(wrap_length)], capture_output=True, text=True, check=True).stdout.split("\n")
+    words = list(range(1, length + 1))
+    segs = [list(map(int, l.split()[1:])) for l in out if l.startswith("seg ")]
+    if wrap_length < 2 or length + 1 <= wrap_length:  # fits (EOS included): passed through untouched
+        assert segs == [words + [0]]
+    else:
+        assert segs == _wrap_ref(words, wrap_length)
+        assert all(len(s) <= wrap_length for s in segs)
+    assert int(next(l for l in out if l.startswith("segments ")).split()[1]) == len(segs)
+    assert int(next(l for l in out if l.startswith("key ")).split()[1]) == _cache_key_ref(3, words + [0])
+    assert "cache ok" in out and "key0 0" in out and "make_cache 1 1" in out
+
+
 @pytest.mark.gpu
 def test_host_layer_matches_ctypes_path(gpu_ctx, tiny_model, shortlist_assets, tmp_path):
     from oracle import slimt_oracle as so

@@ -89,6 +89,31 @@ def test_cross_attention_recompute_equals_cached_path(tiny_gpu, shape, monkeypat
     assert np.array_equal(rc["logits"], cached["logits"])
 
 
+@pytest.mark.parametrize("shape", [(5, 65), (3, 100), (4, 128), (3, 129), (2, 256), (150, 70), (6, 200), (9, 255)])
+def test_long_sentence_cross_attention_recompute_equals_cached_path(tiny_gpu, shape, monkeypatch):
+    """Batches of 65 .. 256 source tokens re-project K/V a sentence at a time (cross_attention_rcl.cu: one or two
+    128-key groups per sentence, softmax across the groups, one weighted-sum chain carried over them; ragged lengths
+    from 1 token up, more sentences than SMs).  Forcing the cached f32 K/V kernel must give the same bits, and both
+    must equal the oracle."""
+    m, orc = tiny_gpu
+    B, T = shape
+    sents = synth.make_sentences(B, (1, T), seed=17 * B + T)
+    sents[0] = synth.make_sentences(1, T, seed=2)[0]
+    sents[-1] = synth.make_sentences(1, max(1, T - 3), seed=3)[0]
+    tokens, lengths = util.pad_batch(sents)
+    lf = 0.25 if B * T <= 1024 else 0.1
+    rc = m.forward(tokens, lengths, want_logits=True, want_alignment=True, limit_factor=lf)
+    monkeypatch.setenv("SLIMT_B200_CROSS", "cached")
+    cached = m.forward(tokens, lengths, want_logits=True, want_alignment=True, limit_factor=lf)
+    monkeypatch.delenv("SLIMT_B200_CROSS")
+    assert np.array_equal(rc["logits"], cached["logits"])
+    assert np.array_equal(rc["alignment"], cached["alignment"])
+    assert np.array_equal(rc["step_tokens"], cached["step_tokens"])
+    if B * T <= 1024:  # the oracle's share of the check, at sizes it finishes in seconds
+        ref = orc.forward(tokens, lengths, keep=True, limit_factor=lf)
+        _compare(rc, ref, lengths, T)
+
+
 @pytest.mark.parametrize("shape", [(37, 32), (9, 20), (70, 5), (130, 1), (5, 33), (7, 64), (40, 48), (3, 2)])
 def test_fused_encoder_attention_equals_split_path(tiny_gpu, shape, monkeypatch):
     """T <= 64 batches run the q/k/v projections and the self-attention as one kernel (enc_attention.cu): tiles of
