@@ -586,6 +586,308 @@ __global__ void __launch_bounds__(kThreadsPair, 1) enc_attention_pair_kernel(con
   if (warp == 2) tmem_dealloc<512>(tmem);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Third generation for T <= 32: one WARP per (sentence, head), register-tiled.  In the kernels above every K and V
+// element reaches a thread as a broadcast 16-byte shared-memory load that feeds four FMAs, and that load -- eight issue
+// cycles per scheduler -- is what the inner loops cost.  Here a tile is four sentences, each in its own 32-row slot of
+// the A operands (its own TMA box), so TMEM lane quadrant qd = sentence qd and the warp that drains a quadrant owns the
+// whole attention of that sentence for the head: no barrier wider than the warp.  The warp parks Q and K transposed
+// ([d][row], conflict-free scalar stores), then works like a register-tiled SGEMM whose every output is still ONE
+// thread's chain in index order:
+//   scores   thread = 4 queries x 8 keys: three 16-byte loads (q quad, two k quads) per 32 FMAs, chains over d;
+//   softmax  a row's 32 keys live in the four adjacent lanes of its query group: max by two shuffles (order-free), exp
+//            elementwise, the row sum handed from lane to lane so that it is one chain in key order, p = e / sum;
+//   P V      P parked transposed in K's place, V (drained from TMEM only now) in Q's place; thread = 4 queries x 8 dims,
+//            three loads per 32 FMAs, chains over the valid keys in order (a masked key adds exactly +0: skipped).
+// Bit-identical to the kernels above and to the split path (test_fused_encoder_attention_equals_split_path).
+constexpr int kWarpBuf = 32 * kStride;  // floats: one [32][36] staging tile
+
+__global__ void __launch_bounds__(kThreadsEa, 1) enc_attention_warp_kernel(const __grid_constant__ EncAttnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  uint8_t* s_a = smem + Smem::a;
+  uint8_t* s_w = smem + Smem::w;
+  float* s_pb = reinterpret_cast<float*>(smem + Smem::pb);
+  uint64_t* exp_tab = reinterpret_cast<uint64_t*>(smem + Smem::exp_tab);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
+  uint64_t* a_full = bars;
+  uint64_t* a_free = bars + 1;
+  uint64_t* w_full = bars + 2;
+  uint64_t* w_free = w_full + kWStages;
+  uint64_t* acc_full = w_free + kWStages;
+  uint64_t* acc_free = acc_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::tmem_slot);
+  static_assert(kConsWarps * 2 * kWarpBuf * 4 <= kSlots * 2 * kStageBytes, "staging tiles fit the K/V region");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.map_aq32), tma_prefetch_desc(&a.map_ak32), tma_prefetch_desc(&a.map_av32);
+    tma_prefetch_desc(&a.map_wq), tma_prefetch_desc(&a.map_wk), tma_prefetch_desc(&a.map_wv);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(a_full, 1), mbar_init(a_free, 1);
+    for (int i = 0; i < kWStages; i++) mbar_init(&w_full[i], 1), mbar_init(&w_free[i], 1);
+    for (int i = 0; i < 4; i++) mbar_init(&acc_full[i], 1), mbar_init(&acc_free[i], 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 3) {
+    exp_tab[lane] = kExp2fTab[lane];
+    for (int i = lane; i < kE; i += 32) {
+      s_pb[i] = a.pb_q[i];
+      s_pb[kE + i] = a.pb_k[i];
+      s_pb[2 * kE + i] = a.pb_v[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();  // the previous kernel's outputs (the quantised x copies) are visible from here on
+  const uint32_t tmem = *tmem_slot;
+
+  const int T = a.T;
+  constexpr int G = 4;  // sentences per tile, one per 32-row slot
+  const int n_tiles = (a.B + G - 1) / G;
+
+  if (warp == 0) {
+    // ===== TMA producer: every sentence's rows into its own slot (rows past the sentence are the next sentence's, or
+    // zero fill past the tensor: they are masked as keys and never stored as queries)
+    if (elect_one()) {
+      const CUtensorMap* map_a[3] = {&a.map_aq32, &a.map_ak32, &a.map_av32};
+      const CUtensorMap* map_w[3] = {&a.map_wq, &a.map_wk, &a.map_wv};
+      uint32_t hc = 0, it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+        mbar_wait(a_free, (it & 1) ^ 1);
+        mbar_expect_tx(a_full, 3 * 32768);
+        for (int m = 0; m < 3; m++)
+          for (int kb = 0; kb < 2; kb++)
+            for (int j = 0; j < G; j++)
+              tma_load_2d(s_a + m * 32768 + kb * 16384 + j * 4096, map_a[m], a_full, kb * 128, (tile * G + j) * T);
+        for (int h = 0; h < kH; h++, hc++) {
+          const uint32_t s = hc % kWStages, ph = (hc / kWStages) & 1;
+          mbar_wait(&w_free[s], ph ^ 1);
+          mbar_expect_tx(&w_full[s], 24576);
+          for (int m = 0; m < 3; m++)
+            for (int kb = 0; kb < 2; kb++)
+              tma_load_2d(s_w + s * 24576 + m * 8192 + kb * 4096, map_w[m], &w_full[s], kb * 128, h * kDH);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (as in enc_attention_kernel)
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_i8(kTileRows, kDH);
+      uint32_t hc = 0, it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+        mbar_wait(a_full, it & 1);
+        for (int h = 0; h < kH; h++, hc++) {
+          const uint32_t s = hc % kWStages;
+          const uint32_t reg = hc & 3;
+          mbar_wait(&w_full[s], (hc / kWStages) & 1);
+          mbar_wait(&acc_free[reg], ((hc >> 2) & 1) ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int m = 0; m < 3; m++) {
+#pragma unroll
+            for (int kb = 0; kb < 2; kb++) {
+              const uint64_t da = make_kmajor_sw128_desc(smem_u32(s_a + m * 32768 + kb * 16384));
+              const uint64_t db = make_kmajor_sw128_desc(smem_u32(s_w + s * 24576 + m * 8192 + kb * 4096));
+#pragma unroll
+              for (int k = 0; k < 4; k++) umma_i8(tmem + reg * 128 + m * 32, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            }
+          }
+          umma_commit(&w_free[s]);
+          umma_commit(&acc_full[reg]);
+        }
+        umma_commit(a_free);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== consumers: warp = (head parity `slot`, sentence qd of the tile)
+    const int slot = (warp - 4) >> 2;
+    const int qd = warp & 3;
+    const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
+    float* buf0 = reinterpret_cast<float*>(smem + Smem::kv) + (warp - 4) * 2 * kWarpBuf;  // Q^T, later V
+    float* buf1 = buf0 + kWarpBuf;                                                         // K^T, later P^T
+    const int ty = lane >> 2, tx = lane & 3;
+    const float ninf = -3.402823466e+38f;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+      const int b = tile * G + qd;
+      const int len = b < a.B ? min(static_cast<int>(__ldg(a.lengths + b)), T) : 0;
+      uint8_t* out_base = a.out_q + static_cast<size_t>(b) * T * kE;
+
+#pragma unroll 1
+      for (int hh = 0; hh < kH / kSlots; hh++) {
+        const int h = hh * kSlots + slot;
+        const uint32_t reg = h & 3;
+        const uint32_t use = it * 2 + (h >> 2);
+        const uint32_t taddr = tmem + lane_sel + reg * 128;
+        mbar_wait(&acc_full[reg], use & 1);
+        tc_fence_after();
+        if (len == 0) {  // no sentence in this slot: hand the region back untouched
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_free[reg]);
+          if (b < a.B)  // an empty sentence: its padded query rows carry quantize(0)
+            for (int i = ty; i < T; i += 8)
+              *reinterpret_cast<uint2*>(out_base + static_cast<size_t>(i) * kE + h * kDH + 8 * tx) = make_uint2(0x7f7f7f7fu, 0x7f7f7f7fu);
+          continue;
+        }
+        {
+          // ---- Q and K of this lane's row -> f32, parked transposed ([d][row]: a row's value of dimension d)
+          uint32_t vq[32], vk[32];
+          tmem_ld32_nowait(taddr, vq);
+          tmem_ld32_nowait(taddr + 32, vk);
+          tmem_ld_wait();
+          const float* pbq = s_pb + h * kDH;
+          const float* pbk = s_pb + kE + h * kDH;
+#pragma unroll
+          for (int d = 0; d < kDH; d += 4) {
+            const float4 pq = *reinterpret_cast<const float4*>(pbq + d);
+            const float4 pk = *reinterpret_cast<const float4*>(pbk + d);
+            buf0[(d + 0) * kStride + lane] = dequant1(static_cast<int>(vq[d]), a.um_q, pq.x);
+            buf0[(d + 1) * kStride + lane] = dequant1(static_cast<int>(vq[d + 1]), a.um_q, pq.y);
+            buf0[(d + 2) * kStride + lane] = dequant1(static_cast<int>(vq[d + 2]), a.um_q, pq.z);
+            buf0[(d + 3) * kStride + lane] = dequant1(static_cast<int>(vq[d + 3]), a.um_q, pq.w);
+            buf1[(d + 0) * kStride + lane] = dequant1(static_cast<int>(vk[d]), a.um_k, pk.x);
+            buf1[(d + 1) * kStride + lane] = dequant1(static_cast<int>(vk[d + 1]), a.um_k, pk.y);
+            buf1[(d + 2) * kStride + lane] = dequant1(static_cast<int>(vk[d + 2]), a.um_k, pk.z);
+            buf1[(d + 3) * kStride + lane] = dequant1(static_cast<int>(vk[d + 3]), a.um_k, pk.w);
+          }
+        }
+        __syncwarp();
+
+        // ---- scores: queries 4 ty .. + 3 against keys 8 tx .. + 7, each a sequential fma chain over d
+        float sc[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+          for (int w = 0; w < 8; w++) sc[u][w] = 0.0f;
+#pragma unroll 8
+        for (int d = 0; d < kDH; d++) {
+          const float4 q4 = *reinterpret_cast<const float4*>(buf0 + d * kStride + 4 * ty);
+          const float4 ka = *reinterpret_cast<const float4*>(buf1 + d * kStride + 8 * tx);
+          const float4 kb = *reinterpret_cast<const float4*>(buf1 + d * kStride + 8 * tx + 4);
+          const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+          const float kv[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int w = 0; w < 8; w++) sc[u][w] = fmaf(qv[u], kv[w], sc[u][w]);
+        }
+        // ---- softmax per query row (TensorOps.cc:282-315): masked keys score -inf and contribute exactly +0
+        float mx[4], sum[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          mx[u] = ninf;
+#pragma unroll
+          for (int w = 0; w < 8; w++) {
+            sc[u][w] = 8 * tx + w < len ? __fmul_rn(a.dk, sc[u][w]) : ninf;
+            mx[u] = fmaxf(mx[u], sc[u][w]);
+          }
+          mx[u] = fmaxf(mx[u], __shfl_xor_sync(0xffffffffu, mx[u], 1));
+          mx[u] = fmaxf(mx[u], __shfl_xor_sync(0xffffffffu, mx[u], 2));
+        }
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+          if (8 * tx + w < len) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) sc[u][w] = expf_glibc_nonpos_tab(__fsub_rn(sc[u][w], mx[u]), exp_tab);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; u++) sc[u][w] = 0.0f;
+          }
+        }
+        // the row sum in key order: lane tx = 0 adds keys 0..7, hands the partial sum to tx = 1, and so on
+#pragma unroll
+        for (int u = 0; u < 4; u++) sum[u] = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const float in = __shfl_sync(0xffffffffu, sum[u], (lane & ~3) | (t > 0 ? t - 1 : 0));
+            if (tx == t) {
+              float s = t == 0 ? 0.0f : in;
+#pragma unroll
+              for (int w = 0; w < 8; w++) s = __fadd_rn(s, sc[u][w]);
+              sum[u] = s;
+            }
+          }
+        }
+        __syncwarp();  // every lane is done reading K^T: its place takes P^T
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          sum[u] = __shfl_sync(0xffffffffu, sum[u], (lane & ~3) | 3);
+          const float rc = rcp_refined(sum[u]), lo = div_guard_lo(sum[u]);
+#pragma unroll
+          for (int w = 0; w < 8; w++) sc[u][w] = div_by_rcp(sc[u][w], sum[u], rc, lo);
+        }
+#pragma unroll
+        for (int w = 0; w < 8; w++)
+          *reinterpret_cast<float4*>(buf1 + (8 * tx + w) * kStride + 4 * ty) = make_float4(sc[0][w], sc[1][w], sc[2][w], sc[3][w]);
+        {
+          // ---- V of this lane's key row -> f32 in Q^T's place (row-major [key][d]); the TMEM region is free after this
+          uint32_t vv[32];
+          tmem_ld32_nowait(taddr + 64, vv);
+          tmem_ld_wait();
+          tc_fence_before();
+          const float* pbv = s_pb + 2 * kE + h * kDH;
+#pragma unroll
+          for (int d = 0; d < kDH; d += 4) {
+            const float4 pv = *reinterpret_cast<const float4*>(pbv + d);
+            *reinterpret_cast<float4*>(buf0 + lane * kStride + d) =
+                make_float4(dequant1(static_cast<int>(vv[d]), a.um_v, pv.x), dequant1(static_cast<int>(vv[d + 1]), a.um_v, pv.y),
+                            dequant1(static_cast<int>(vv[d + 2]), a.um_v, pv.z), dequant1(static_cast<int>(vv[d + 3]), a.um_v, pv.w));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_free[reg]);
+
+        // ---- P V: queries 4 ty .. + 3, dims 8 tx .. + 7, one chain per output over the valid keys in order
+        float acc[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+          for (int w = 0; w < 8; w++) acc[u][w] = 0.0f;
+#pragma unroll 4
+        for (int j = 0; j < len; j++) {
+          const float4 p4 = *reinterpret_cast<const float4*>(buf1 + j * kStride + 4 * ty);
+          const float4 va = *reinterpret_cast<const float4*>(buf0 + j * kStride + 8 * tx);
+          const float4 vb = *reinterpret_cast<const float4*>(buf0 + j * kStride + 8 * tx + 4);
+          const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+          const float vv[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int w = 0; w < 8; w++) acc[u][w] = fmaf(pv[u], vv[w], acc[u][w]);
+        }
+        // ---- Wo's operand: 8 bytes per (query row, thread); padded query rows carry quantize(0) like the split path
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = 4 * ty + u;
+          if (i < T) {
+            uint2 o = make_uint2(0x7f7f7f7fu, 0x7f7f7f7fu);
+            if (i < len) {
+              o.x = pack4(quantize1(acc[u][0], a.aq_out), quantize1(acc[u][1], a.aq_out), quantize1(acc[u][2], a.aq_out),
+                          quantize1(acc[u][3], a.aq_out));
+              o.y = pack4(quantize1(acc[u][4], a.aq_out), quantize1(acc[u][5], a.aq_out), quantize1(acc[u][6], a.aq_out),
+                          quantize1(acc[u][7], a.aq_out));
+            }
+            *reinterpret_cast<uint2*>(out_base + static_cast<size_t>(i) * kE + h * kDH + 8 * tx) = o;
+          }
+        }
+        __syncwarp();  // the staging tiles are rewritten by the next head
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
 template <int TMAX>
 int launch_t(const EncAttnArgs& a, int grid, cudaStream_t stream) {
   auto kern = enc_attention_kernel<TMAX>;
@@ -602,10 +904,17 @@ int launch_enc_attention(const EncAttnArgs& a, int num_sms, cudaStream_t stream)
   const int G = kTileRows / a.T;
   const int tiles = (a.B + G - 1) / G;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  static const bool single = [] {
-    const char* e = getenv("SLIMT_B200_ENCATTN");  // =single keeps one thread per query row at T <= 32 (A/B, cross-check)
-    return e && strcmp(e, "single") == 0;
+  static const int variant = [] {
+    const char* e = getenv("SLIMT_B200_ENCATTN");  // =single / =pair keep the earlier T <= 32 kernels (A/B, cross-check)
+    return e && strcmp(e, "single") == 0 ? 1 : e && strcmp(e, "pair") == 0 ? 2 : 0;
   }();
+  const bool single = variant == 1;
+  if (a.T <= 32 && variant == 0) {
+    const int tiles4 = (a.B + 3) / 4;
+    if (ensure_dyn_smem(enc_attention_warp_kernel, Smem::total) != cudaSuccess) return 1;
+    return launch_pdl(enc_attention_warp_kernel, dim3(tiles4 < num_sms ? tiles4 : num_sms), dim3(kThreadsEa), Smem::total, stream,
+                      a) != cudaSuccess;
+  }
   if (a.T <= 32 && !single) {
     if (ensure_dyn_smem(enc_attention_pair_kernel, SmemPair::total) != cudaSuccess) return 1;
     return launch_pdl(enc_attention_pair_kernel, dim3(grid), dim3(kThreadsPair), SmemPair::total, stream, a) != cudaSuccess;

@@ -736,10 +736,10 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
   const bool attn_rowwise = (sa_env && strcmp(sa_env, "rowwise") == 0) || (T <= 64 && !(sa_env && strcmp(sa_env, "tiled") == 0));
   const bool attn_fused = enc_attention_supported(E, H, dh, T) &&
                           !(sa_env && (strcmp(sa_env, "split") == 0 || strcmp(sa_env, "rowwise") == 0 || strcmp(sa_env, "tiled") == 0));
-  CUtensorMap map_qa[3];
+  CUtensorMap map_qa[3], map_qa32[3];
   if (attn_fused)
     for (int i = 0; i < 3; i++)
-      if (c.make_map(&map_qa[i], qa[i], R, E, 128)) return 1;
+      if (c.make_map(&map_qa[i], qa[i], R, E, 128) || c.make_map(&map_qa32[i], qa[i], R, E, 32)) return 1;
 
   // debugging aid: SLIMT_B200_TRACE=<file> records the phase stamps of the row-tile kernels: the encoder's first FFN
   // launch (first tile of every CTA) and the two decoder kernels of layer 0 in decode step 3
@@ -768,6 +768,7 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
       // q/k/v projections + scaled dot-product attention in one kernel: Q, K, V stay on the SM (enc_attention.cu)
       EncAttnArgs k{};
       k.map_aq = map_qa[0], k.map_ak = map_qa[1], k.map_av = map_qa[2];
+      k.map_aq32 = map_qa32[0], k.map_ak32 = map_qa32[1], k.map_av32 = map_qa32[2];
       k.map_wq = L.self.q.map32, k.map_wk = L.self.k.map32, k.map_wv = L.self.v.map32;
       k.pb_q = L.self.q.pb, k.pb_k = L.self.k.pb, k.pb_v = L.self.v.pb;
       k.um_q = L.self.q.um, k.um_k = L.self.k.um, k.um_v = L.self.v.um;

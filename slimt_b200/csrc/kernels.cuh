@@ -70,6 +70,7 @@ int launch_cross_attention_rcl(const CrossRcArgs& a, int num_sms, cudaStream_t s
 // Bit-identical to launch_gemm_i8(EPI_F32) x 3 followed by launch_self_attention.
 struct EncAttnArgs {
   CUtensorMap map_aq, map_ak, map_av;  // u8 [B*T][E], box {128 B, 128 rows}: x quantised with Wq's / Wk's / Wv's a_quant
+  CUtensorMap map_aq32, map_ak32, map_av32;  // the same tensors with box {128 B, 32 rows} (T <= 32: a box per sentence)
   CUtensorMap map_wq, map_wk, map_wv;  // s8 [E][E], box {128 B, 32 rows}
   const float* pb_q;                   // prepared biases
   const float* pb_k;
