@@ -412,6 +412,21 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
         }
         if constexpr (KB > 1) named_bar_sync(2 + kj * 4 + sub, KB * 32);
         else __syncwarp();
+        if constexpr (KB == 1) {
+          // one chain per head is enough: the lower half-warp forms head h0's sum, the upper half head h0 + 1's
+          const float* pr = prow + (lane >> 4) * kRow;
+          float s = 0.0f;
+#pragma unroll
+          for (int l = 0; l < kRow; l += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(pr + l);
+            s = __fadd_rn(s, t.x);
+            s = __fadd_rn(s, t.y);
+            s = __fadd_rn(s, t.z);
+            s = __fadd_rn(s, t.w);
+          }
+          sum[0] = __shfl_sync(0xffffffffu, s, 0);
+          sum[1] = __shfl_sync(0xffffffffu, s, 16);
+        } else {
 #pragma unroll
         for (int l = 0; l < kRow; l += 4) {
 #pragma unroll
@@ -422,6 +437,7 @@ __global__ void __launch_bounds__(kThreadsRc, 1) cross_attention_rc_kernel(const
             sum[hh] = __fadd_rn(sum[hh], t.z);
             sum[hh] = __fadd_rn(sum[hh], t.w);
           }
+        }
         }
         if constexpr (KB > 1) named_bar_sync(2 + kj * 4 + sub, KB * 32);  // every warp of the sentence has read the e's
         else __syncwarp();

@@ -163,27 +163,33 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
           // the previous step's bookkeeping for the tile's rows (finalize_step_kernel's, thread = row), then the
           // words' embedding rows -> x (registers) and its two quantised operands (shared memory, UMMA layout)
           uint32_t* s_tok = reinterpret_cast<uint32_t*>(stats);  // free until the LayerNorm statistics
+          // Only packed best -> shortlist -> token is on the path to the x operands: the row's other inputs are requested
+          // alongside the first load, and record() itself (Model.cc:127-137) runs after the operands are handed over.
+          uint32_t word = 0, was_done = 1, len_before = 0;
+          const int bk = row0 + et;
           if (et < kR) {
-            const int b = row0 + et;
             uint32_t tok = 0;
-            if (b < a.M) {
-              const unsigned long long packed = a.best[b];
+            if (bk < a.M) {
+              const unsigned long long packed = a.best[bk];
+              was_done = a.done[bk];
+              len_before = a.tgt_len[bk];
+              const uint32_t forced = a.forced ? a.forced[static_cast<size_t>(a.prev_step) * a.M + bk] : 0u;
               const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(packed & 0xFFFFFFFFull);
-              const uint32_t word = a.shortlist ? a.shortlist[idx] : idx;
-              a.step_tokens[static_cast<size_t>(a.prev_step) * a.M + b] = word;
-              if (!a.done[b]) {  // record(), slimt/Model.cc:127-137: append unless already finished
-                a.tgt_len[b] += 1;
-                if (word == a.eos_id) {
-                  a.done[b] = 1;
-                  atomicAdd(a.n_done, 1);
-                }
-              }
-              a.best[b] = 0ull;
-              tok = a.forced ? a.forced[static_cast<size_t>(a.prev_step) * a.M + b] : word;
+              word = a.shortlist ? a.shortlist[idx] : idx;
+              tok = a.forced ? forced : word;
             }
             s_tok[et] = tok;
           }
+          if (et == 0) SB_TRACE(a, 15);
           named_bar_sync(1, kEpiThreads);
+          if (et == 0) SB_TRACE(a, 16);
+          // swizzled byte offset of (row, f) inside an operand k-block is row * 128 + xo[row & 7] (rows_common.cuh: opnd_off)
+          uint32_t xo[8];
+          {
+            const int kk = q * 32 + lane;
+#pragma unroll
+            for (int i = 0; i < 8; i++) xo[i] = static_cast<uint32_t>((((kk >> 4) ^ i) << 4) + (kk & 15));
+          }
 #pragma unroll
           for (int mb = 0; mb < EM; mb++) {
             const int f = mb * 128 + q * 32 + lane;
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
               const float w = static_cast<float>(a.emb_q[static_cast<size_t>(s_tok[row]) * E + f]);
               const float y = __fadd_rn(__fmul_rn(__fmul_rn(w, a.inv_qm), a.sqrt_e), ps);
               xv[mb][r] = y;
-              const uint32_t off = opnd_off<kR>(row, f);
+              const uint32_t off = static_cast<uint32_t>(mb * kOpK + row * 128) + xo[r];  // row & 7 == r: rq * 8 is a multiple of 8
               opnd_xf[off] = static_cast<uint8_t>(quantize1(y, a.aq_xf));
               opnd_xw[off] = static_cast<uint8_t>(quantize1(y, a.aq_xw));
             }
@@ -202,6 +208,18 @@ __global__ void __launch_bounds__(kThreads, 1) dec_ssru_kernel(const __grid_cons
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(x_full);
+          if (et == 0) SB_TRACE(a, 17);
+          if (et < kR && bk < a.M) {  // record(): append unless already finished; re-arm the packed best
+            a.step_tokens[static_cast<size_t>(a.prev_step) * a.M + bk] = word;
+            if (!was_done) {
+              a.tgt_len[bk] = len_before + 1;
+              if (word == a.eos_id) {
+                a.done[bk] = 1;
+                atomicAdd(a.n_done, 1);
+              }
+            }
+            a.best[bk] = 0ull;
+          }
         }
 #pragma unroll
         for (int mb = 0; mb < EM; mb++) {

@@ -29,7 +29,8 @@ for i, nm in enumerate(FINE):
     FFN[88 + i] = f"fine FFN2 k-step 3 mb 1: {nm}"
 SSRU = {0: "start", 1: "setup done", 2: "mma: x landed", 3: "mma: Wf,W issued", 14: "epi: state/x rows loaded", 4: "epi: Wf,W done",
         5: "epi: x parked", 6: "epi: LN stats", 7: "epi: h operand ready", 8: "mma: h seen", 9: "mma: Wq issued", 10: "epi: Wq done",
-        11: "epi: q written", 13: "exit"}
+        11: "epi: q written", 13: "exit", 15: "epi: row 0's bookkeeping done", 16: "epi: tile's tokens known",
+        17: "epi: x operands written"}
 CROSS = {0: "start"}
 RC = ["group: q stored", "after group barrier", "K accumulators ready", "K in registers", "scores formed", "softmax done",
       "after mid barrier", "V accumulators ready", "V in registers", "V sums formed", "V emitted"]
