@@ -600,24 +600,44 @@ __global__ void __launch_bounds__(kThreadsPair, 1) enc_attention_pair_kernel(con
 //   P V      P parked transposed in K's place, V (drained from TMEM only now) in Q's place; thread = 4 queries x 8 dims,
 //            three loads per 32 FMAs, chains over the valid keys in order (a masked key adds exactly +0: skipped).
 // Bit-identical to the kernels above and to the split path (test_fused_encoder_attention_equals_split_path).
-constexpr int kWarpBuf = 32 * kStride;  // floats: one [32][36] staging tile
+// Twelve consumer warps (three per scheduler: the phases of a unit are latency chains, the third warp fills their gaps)
+// take the CTA's (tile, head) units round-robin.  That many staging tiles only fit because they are unpadded
+// ([32][32] floats with XOR-swizzled 16-byte chunks where a padded row used to avoid the bank conflicts) and the weight
+// ring has ONE stage: the MMA of a head is ~1 k cycles of a ~9 k-cycle unit, its weights need no prefetch distance.
+constexpr int kWSlots = 3;
+constexpr int kWWarps = 4 * kWSlots;
+constexpr int kThreadsW = 128 + 32 * kWWarps;
+constexpr int kWarpBuf = 32 * 32;  // floats: one [32][32] staging tile
 
-__global__ void __launch_bounds__(kThreadsEa, 1) enc_attention_warp_kernel(const __grid_constant__ EncAttnArgs a) {
+struct SmemW {
+  static constexpr int a = 0;                              // 3 operands x 2 k-blocks x [128 rows x 128 B]
+  static constexpr int w = a + 3 * 32768;                  // 3 matrices x 2 k-blocks x [32 features x 128 B], one stage
+  static constexpr int kv = w + 24576;                     // per warp: two staging tiles
+  static constexpr int pb = kv + kWWarps * 2 * kWarpBuf * 4;  // f32 [3][256]
+  static constexpr int exp_tab = pb + 3 * kE * 4;          // u64 [32]
+  static constexpr int bars = exp_tab + 32 * 8;
+  // a_full a_free w_full w_free acc_full[4] acc_free[4]
+  static constexpr int n_bars = 4 + 8;
+  static constexpr int tmem_slot = bars + n_bars * 8;
+  static constexpr int total = tmem_slot + 16 + 1024;
+};
+static_assert(SmemW::total <= 227 * 1024, "shared memory budget");
+
+__global__ void __launch_bounds__(kThreadsW, 1) enc_attention_warp_kernel(const __grid_constant__ EncAttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
-  uint8_t* s_a = smem + Smem::a;
-  uint8_t* s_w = smem + Smem::w;
-  float* s_pb = reinterpret_cast<float*>(smem + Smem::pb);
-  uint64_t* exp_tab = reinterpret_cast<uint64_t*>(smem + Smem::exp_tab);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
+  uint8_t* s_a = smem + SmemW::a;
+  uint8_t* s_w = smem + SmemW::w;
+  float* s_pb = reinterpret_cast<float*>(smem + SmemW::pb);
+  uint64_t* exp_tab = reinterpret_cast<uint64_t*>(smem + SmemW::exp_tab);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SmemW::bars);
   uint64_t* a_full = bars;
   uint64_t* a_free = bars + 1;
   uint64_t* w_full = bars + 2;
-  uint64_t* w_free = w_full + kWStages;
-  uint64_t* acc_full = w_free + kWStages;
+  uint64_t* w_free = bars + 3;
+  uint64_t* acc_full = bars + 4;
   uint64_t* acc_free = acc_full + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::tmem_slot);
-  static_assert(kConsWarps * 2 * kWarpBuf * 4 <= kSlots * 2 * kStageBytes, "staging tiles fit the K/V region");
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SmemW::tmem_slot);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -625,8 +645,7 @@ __global__ void __launch_bounds__(kThreadsEa, 1) enc_attention_warp_kernel(const
     tma_prefetch_desc(&a.map_wq), tma_prefetch_desc(&a.map_wk), tma_prefetch_desc(&a.map_wv);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(a_full, 1), mbar_init(a_free, 1);
-    for (int i = 0; i < kWStages; i++) mbar_init(&w_full[i], 1), mbar_init(&w_free[i], 1);
+    for (int i = 0; i < 4; i++) mbar_init(&bars[i], 1);
     for (int i = 0; i < 4; i++) mbar_init(&acc_full[i], 1), mbar_init(&acc_free[i], 4);
     fence_barrier_init();
   }
@@ -665,26 +684,23 @@ __global__ void __launch_bounds__(kThreadsEa, 1) enc_attention_warp_kernel(const
             for (int j = 0; j < G; j++)
               tma_load_2d(s_a + m * 32768 + kb * 16384 + j * 4096, map_a[m], a_full, kb * 128, (tile * G + j) * T);
         for (int h = 0; h < kH; h++, hc++) {
-          const uint32_t s = hc % kWStages, ph = (hc / kWStages) & 1;
-          mbar_wait(&w_free[s], ph ^ 1);
-          mbar_expect_tx(&w_full[s], 24576);
+          mbar_wait(w_free, (hc & 1) ^ 1);
+          mbar_expect_tx(w_full, 24576);
           for (int m = 0; m < 3; m++)
-            for (int kb = 0; kb < 2; kb++)
-              tma_load_2d(s_w + s * 24576 + m * 8192 + kb * 4096, map_w[m], &w_full[s], kb * 128, h * kDH);
+            for (int kb = 0; kb < 2; kb++) tma_load_2d(s_w + m * 8192 + kb * 4096, map_w[m], w_full, kb * 128, h * kDH);
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (as in enc_attention_kernel)
+    // ===== MMA issuer: per head, D_q | D_k | D_v = (x quantised for that projection) x (the head's 32 features)
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_i8(kTileRows, kDH);
       uint32_t hc = 0, it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
         mbar_wait(a_full, it & 1);
         for (int h = 0; h < kH; h++, hc++) {
-          const uint32_t s = hc % kWStages;
           const uint32_t reg = hc & 3;
-          mbar_wait(&w_full[s], (hc / kWStages) & 1);
+          mbar_wait(w_full, hc & 1);
           mbar_wait(&acc_free[reg], ((hc >> 2) & 1) ^ 1);
           tc_fence_after();
 #pragma unroll
@@ -692,194 +708,205 @@ __global__ void __launch_bounds__(kThreadsEa, 1) enc_attention_warp_kernel(const
 #pragma unroll
             for (int kb = 0; kb < 2; kb++) {
               const uint64_t da = make_kmajor_sw128_desc(smem_u32(s_a + m * 32768 + kb * 16384));
-              const uint64_t db = make_kmajor_sw128_desc(smem_u32(s_w + s * 24576 + m * 8192 + kb * 4096));
+              const uint64_t db = make_kmajor_sw128_desc(smem_u32(s_w + m * 8192 + kb * 4096));
 #pragma unroll
               for (int k = 0; k < 4; k++) umma_i8(tmem + reg * 128 + m * 32, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
             }
           }
-          umma_commit(&w_free[s]);
+          umma_commit(w_free);
           umma_commit(&acc_full[reg]);
         }
         umma_commit(a_free);
       }
     }
   } else if (warp >= 4) {
-    // ===== consumers: warp = (head parity `slot`, sentence qd of the tile)
+    // ===== consumers: warp = (slot, sentence qd of the tile); slot s takes the CTA's units s, s + 3, s + 6, ...
+    // (unit u = head u % 8 of the CTA's tile u / 8; its accumulators sit in TMEM region u % 4)
     const int slot = (warp - 4) >> 2;
     const int qd = warp & 3;
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
-    float* buf0 = reinterpret_cast<float*>(smem + Smem::kv) + (warp - 4) * 2 * kWarpBuf;  // Q^T, later V
-    float* buf1 = buf0 + kWarpBuf;                                                         // K^T, later P^T
+    float* buf0 = reinterpret_cast<float*>(smem + SmemW::kv) + (warp - 4) * 2 * kWarpBuf;  // Q^T, later V
+    float* buf1 = buf0 + kWarpBuf;                                                          // K^T, later P^T
     const int ty = lane >> 2, tx = lane & 3;
     const float ninf = -3.402823466e+38f;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
-      const int b = tile * G + qd;
-      const int len = b < a.B ? min(static_cast<int>(__ldg(a.lengths + b)), T) : 0;
-      uint8_t* out_base = a.out_q + static_cast<size_t>(b) * T * kE;
-
+    const int my_tiles = blockIdx.x < static_cast<unsigned>(n_tiles) ? (n_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+    const int n_units = my_tiles * kH;
+    auto sentence_of = [&](int u) { return (static_cast<int>(blockIdx.x) + (u >> 3) * static_cast<int>(gridDim.x)) * G + qd; };
+    // the next unit's sentence length is requested a unit ahead (raw; clamped at use)
+    int len_nx = 0;
+    if (slot < n_units) {
+      const int b = sentence_of(slot);
+      len_nx = b < a.B ? static_cast<int>(__ldg(a.lengths + b)) : 0;
+    }
 #pragma unroll 1
-      for (int hh = 0; hh < kH / kSlots; hh++) {
-        const int h = hh * kSlots + slot;
-        const uint32_t reg = h & 3;
-        const uint32_t use = it * 2 + (h >> 2);
-        const uint32_t taddr = tmem + lane_sel + reg * 128;
-        mbar_wait(&acc_full[reg], use & 1);
-        tc_fence_after();
-        if (len == 0) {  // no sentence in this slot: hand the region back untouched
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_free[reg]);
-          if (b < a.B)  // an empty sentence: its padded query rows carry quantize(0)
-            for (int i = ty; i < T; i += 8)
-              *reinterpret_cast<uint2*>(out_base + static_cast<size_t>(i) * kE + h * kDH + 8 * tx) = make_uint2(0x7f7f7f7fu, 0x7f7f7f7fu);
-          continue;
-        }
-        {
-          // ---- Q and K of this lane's row -> f32, parked transposed ([d][row]: a row's value of dimension d)
-          uint32_t vq[32], vk[32];
-          tmem_ld32_nowait(taddr, vq);
-          tmem_ld32_nowait(taddr + 32, vk);
-          tmem_ld_wait();
-          const float* pbq = s_pb + h * kDH;
-          const float* pbk = s_pb + kE + h * kDH;
-#pragma unroll
-          for (int d = 0; d < kDH; d += 4) {
-            const float4 pq = *reinterpret_cast<const float4*>(pbq + d);
-            const float4 pk = *reinterpret_cast<const float4*>(pbk + d);
-            buf0[(d + 0) * kStride + lane] = dequant1(static_cast<int>(vq[d]), a.um_q, pq.x);
-            buf0[(d + 1) * kStride + lane] = dequant1(static_cast<int>(vq[d + 1]), a.um_q, pq.y);
-            buf0[(d + 2) * kStride + lane] = dequant1(static_cast<int>(vq[d + 2]), a.um_q, pq.z);
-            buf0[(d + 3) * kStride + lane] = dequant1(static_cast<int>(vq[d + 3]), a.um_q, pq.w);
-            buf1[(d + 0) * kStride + lane] = dequant1(static_cast<int>(vk[d]), a.um_k, pk.x);
-            buf1[(d + 1) * kStride + lane] = dequant1(static_cast<int>(vk[d + 1]), a.um_k, pk.y);
-            buf1[(d + 2) * kStride + lane] = dequant1(static_cast<int>(vk[d + 2]), a.um_k, pk.z);
-            buf1[(d + 3) * kStride + lane] = dequant1(static_cast<int>(vk[d + 3]), a.um_k, pk.w);
-          }
-        }
-        __syncwarp();
-
-        // ---- scores: queries 4 ty .. + 3 against keys 8 tx .. + 7, each a sequential fma chain over d
-        float sc[4][8];
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-#pragma unroll
-          for (int w = 0; w < 8; w++) sc[u][w] = 0.0f;
-#pragma unroll 8
-        for (int d = 0; d < kDH; d++) {
-          const float4 q4 = *reinterpret_cast<const float4*>(buf0 + d * kStride + 4 * ty);
-          const float4 ka = *reinterpret_cast<const float4*>(buf1 + d * kStride + 8 * tx);
-          const float4 kb = *reinterpret_cast<const float4*>(buf1 + d * kStride + 8 * tx + 4);
-          const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
-          const float kv[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
-#pragma unroll
-          for (int u = 0; u < 4; u++)
-#pragma unroll
-            for (int w = 0; w < 8; w++) sc[u][w] = fmaf(qv[u], kv[w], sc[u][w]);
-        }
-        // ---- softmax per query row (TensorOps.cc:282-315): masked keys score -inf and contribute exactly +0
-        float mx[4], sum[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          mx[u] = ninf;
-#pragma unroll
-          for (int w = 0; w < 8; w++) {
-            sc[u][w] = 8 * tx + w < len ? __fmul_rn(a.dk, sc[u][w]) : ninf;
-            mx[u] = fmaxf(mx[u], sc[u][w]);
-          }
-          mx[u] = fmaxf(mx[u], __shfl_xor_sync(0xffffffffu, mx[u], 1));
-          mx[u] = fmaxf(mx[u], __shfl_xor_sync(0xffffffffu, mx[u], 2));
-        }
-#pragma unroll
-        for (int w = 0; w < 8; w++) {
-          if (8 * tx + w < len) {
-#pragma unroll
-            for (int u = 0; u < 4; u++) sc[u][w] = expf_glibc_nonpos_tab(__fsub_rn(sc[u][w], mx[u]), exp_tab);
-          } else {
-#pragma unroll
-            for (int u = 0; u < 4; u++) sc[u][w] = 0.0f;
-          }
-        }
-        // the row sum in key order: lane tx = 0 adds keys 0..7, hands the partial sum to tx = 1, and so on
-#pragma unroll
-        for (int u = 0; u < 4; u++) sum[u] = 0.0f;
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const float in = __shfl_sync(0xffffffffu, sum[u], (lane & ~3) | (t > 0 ? t - 1 : 0));
-            if (tx == t) {
-              float s = t == 0 ? 0.0f : in;
-#pragma unroll
-              for (int w = 0; w < 8; w++) s = __fadd_rn(s, sc[u][w]);
-              sum[u] = s;
-            }
-          }
-        }
-        __syncwarp();  // every lane is done reading K^T: its place takes P^T
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          sum[u] = __shfl_sync(0xffffffffu, sum[u], (lane & ~3) | 3);
-          const float rc = rcp_refined(sum[u]), lo = div_guard_lo(sum[u]);
-#pragma unroll
-          for (int w = 0; w < 8; w++) sc[u][w] = div_by_rcp(sc[u][w], sum[u], rc, lo);
-        }
-#pragma unroll
-        for (int w = 0; w < 8; w++)
-          *reinterpret_cast<float4*>(buf1 + (8 * tx + w) * kStride + 4 * ty) = make_float4(sc[0][w], sc[1][w], sc[2][w], sc[3][w]);
-        {
-          // ---- V of this lane's key row -> f32 in Q^T's place (row-major [key][d]); the TMEM region is free after this
-          uint32_t vv[32];
-          tmem_ld32_nowait(taddr + 64, vv);
-          tmem_ld_wait();
-          tc_fence_before();
-          const float* pbv = s_pb + 2 * kE + h * kDH;
-#pragma unroll
-          for (int d = 0; d < kDH; d += 4) {
-            const float4 pv = *reinterpret_cast<const float4*>(pbv + d);
-            *reinterpret_cast<float4*>(buf0 + lane * kStride + d) =
-                make_float4(dequant1(static_cast<int>(vv[d]), a.um_v, pv.x), dequant1(static_cast<int>(vv[d + 1]), a.um_v, pv.y),
-                            dequant1(static_cast<int>(vv[d + 2]), a.um_v, pv.z), dequant1(static_cast<int>(vv[d + 3]), a.um_v, pv.w));
-          }
-        }
+    for (int u = slot; u < n_units; u += kWSlots) {
+      const int h = u & 7;
+      const uint32_t reg = u & 3;
+      const int b = sentence_of(u);
+      const int len = min(len_nx, T);
+      if (u + kWSlots < n_units) {
+        const int bn = sentence_of(u + kWSlots);
+        len_nx = bn < a.B ? static_cast<int>(__ldg(a.lengths + bn)) : 0;
+      }
+      uint8_t* out_base = a.out_q + static_cast<size_t>(b) * T * kE;
+      const uint32_t taddr = tmem + lane_sel + reg * 128;
+      mbar_wait(&acc_full[reg], (u >> 2) & 1);
+      tc_fence_after();
+      if (len == 0) {  // no sentence in this slot (or an empty one): hand the region back untouched
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_free[reg]);
-
-        // ---- P V: queries 4 ty .. + 3, dims 8 tx .. + 7, one chain per output over the valid keys in order
-        float acc[4][8];
+        if (b < a.B)  // an empty sentence: its padded query rows carry quantize(0)
+          for (int i = ty; i < T; i += 8)
+            *reinterpret_cast<uint2*>(out_base + static_cast<size_t>(i) * kE + h * kDH + 8 * tx) = make_uint2(0x7f7f7f7fu, 0x7f7f7f7fu);
+        continue;
+      }
+      {
+        // ---- Q and K of this lane's row -> f32, parked transposed ([d][row]: a row's value of dimension d)
+        uint32_t vq[32], vk[32];
+        tmem_ld32_nowait(taddr, vq);
+        tmem_ld32_nowait(taddr + 32, vk);
+        tmem_ld_wait();
+        const float* pbq = s_pb + h * kDH;
+        const float* pbk = s_pb + kE + h * kDH;
 #pragma unroll
-        for (int u = 0; u < 4; u++)
-#pragma unroll
-          for (int w = 0; w < 8; w++) acc[u][w] = 0.0f;
-#pragma unroll 4
-        for (int j = 0; j < len; j++) {
-          const float4 p4 = *reinterpret_cast<const float4*>(buf1 + j * kStride + 4 * ty);
-          const float4 va = *reinterpret_cast<const float4*>(buf0 + j * kStride + 8 * tx);
-          const float4 vb = *reinterpret_cast<const float4*>(buf0 + j * kStride + 8 * tx + 4);
-          const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
-          const float vv[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-#pragma unroll
-          for (int u = 0; u < 4; u++)
-#pragma unroll
-            for (int w = 0; w < 8; w++) acc[u][w] = fmaf(pv[u], vv[w], acc[u][w]);
+        for (int d = 0; d < kDH; d += 4) {
+          const float4 pq = *reinterpret_cast<const float4*>(pbq + d);
+          const float4 pk = *reinterpret_cast<const float4*>(pbk + d);
+          buf0[(d + 0) * 32 + lane] = dequant1(static_cast<int>(vq[d]), a.um_q, pq.x);
+          buf0[(d + 1) * 32 + lane] = dequant1(static_cast<int>(vq[d + 1]), a.um_q, pq.y);
+          buf0[(d + 2) * 32 + lane] = dequant1(static_cast<int>(vq[d + 2]), a.um_q, pq.z);
+          buf0[(d + 3) * 32 + lane] = dequant1(static_cast<int>(vq[d + 3]), a.um_q, pq.w);
+          buf1[(d + 0) * 32 + lane] = dequant1(static_cast<int>(vk[d]), a.um_k, pk.x);
+          buf1[(d + 1) * 32 + lane] = dequant1(static_cast<int>(vk[d + 1]), a.um_k, pk.y);
+          buf1[(d + 2) * 32 + lane] = dequant1(static_cast<int>(vk[d + 2]), a.um_k, pk.z);
+          buf1[(d + 3) * 32 + lane] = dequant1(static_cast<int>(vk[d + 3]), a.um_k, pk.w);
         }
-        // ---- Wo's operand: 8 bytes per (query row, thread); padded query rows carry quantize(0) like the split path
+      }
+      __syncwarp();
+
+      // ---- scores: queries 4 ty .. + 3 against keys 8 tx .. + 7, each a sequential fma chain over d
+      float sc[4][8];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int i = 4 * ty + u;
-          if (i < T) {
-            uint2 o = make_uint2(0x7f7f7f7fu, 0x7f7f7f7fu);
-            if (i < len) {
-              o.x = pack4(quantize1(acc[u][0], a.aq_out), quantize1(acc[u][1], a.aq_out), quantize1(acc[u][2], a.aq_out),
-                          quantize1(acc[u][3], a.aq_out));
-              o.y = pack4(quantize1(acc[u][4], a.aq_out), quantize1(acc[u][5], a.aq_out), quantize1(acc[u][6], a.aq_out),
-                          quantize1(acc[u][7], a.aq_out));
-            }
-            *reinterpret_cast<uint2*>(out_base + static_cast<size_t>(i) * kE + h * kDH + 8 * tx) = o;
+      for (int x = 0; x < 4; x++)
+#pragma unroll
+        for (int w = 0; w < 8; w++) sc[x][w] = 0.0f;
+#pragma unroll 8
+      for (int d = 0; d < kDH; d++) {
+        const float4 q4 = *reinterpret_cast<const float4*>(buf0 + d * 32 + 4 * ty);
+        const float4 ka = *reinterpret_cast<const float4*>(buf1 + d * 32 + 8 * tx);
+        const float4 kb = *reinterpret_cast<const float4*>(buf1 + d * 32 + 8 * tx + 4);
+        const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+        const float kv[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+#pragma unroll
+        for (int x = 0; x < 4; x++)
+#pragma unroll
+          for (int w = 0; w < 8; w += 2) ffma2(sc[x][w], sc[x][w + 1], qv[x], qv[x], kv[w], kv[w + 1]);
+      }
+      // ---- softmax per query row (TensorOps.cc:282-315): masked keys score -inf and contribute exactly +0
+      float mx[4], sum[4];
+#pragma unroll
+      for (int x = 0; x < 4; x++) {
+        mx[x] = ninf;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+          sc[x][w] = 8 * tx + w < len ? __fmul_rn(a.dk, sc[x][w]) : ninf;
+          mx[x] = fmaxf(mx[x], sc[x][w]);
+        }
+        mx[x] = fmaxf(mx[x], __shfl_xor_sync(0xffffffffu, mx[x], 1));
+        mx[x] = fmaxf(mx[x], __shfl_xor_sync(0xffffffffu, mx[x], 2));
+      }
+#pragma unroll
+      for (int w = 0; w < 8; w++) {
+        if (8 * tx + w < len) {
+#pragma unroll
+          for (int x = 0; x < 4; x++) sc[x][w] = expf_glibc_nonpos_tab(__fsub_rn(sc[x][w], mx[x]), exp_tab);
+        } else {
+#pragma unroll
+          for (int x = 0; x < 4; x++) sc[x][w] = 0.0f;
+        }
+      }
+      // the row sum in key order: lane tx = 0 adds keys 0..7, hands the partial sum to tx = 1, and so on
+#pragma unroll
+      for (int x = 0; x < 4; x++) sum[x] = 0.0f;
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+          const float in = __shfl_sync(0xffffffffu, sum[x], (lane & ~3) | (t > 0 ? t - 1 : 0));
+          if (tx == t) {
+            float acc1 = t == 0 ? 0.0f : in;
+#pragma unroll
+            for (int w = 0; w < 8; w++) acc1 = __fadd_rn(acc1, sc[x][w]);
+            sum[x] = acc1;
           }
         }
-        __syncwarp();  // the staging tiles are rewritten by the next head
       }
+      __syncwarp();  // every lane is done reading K^T: its place takes P^T
+#pragma unroll
+      for (int x = 0; x < 4; x++) {
+        sum[x] = __shfl_sync(0xffffffffu, sum[x], (lane & ~3) | 3);
+        const float rc = rcp_refined(sum[x]), lo = div_guard_lo(sum[x]);
+#pragma unroll
+        for (int w = 0; w < 8; w++) sc[x][w] = div_by_rcp(sc[x][w], sum[x], rc, lo);
+      }
+      // P^T[key][query quad]: quad ty of key row j sits at chunk ty ^ 2 (j / 8) (conflict-free stores and loads)
+#pragma unroll
+      for (int w = 0; w < 8; w++)
+        *reinterpret_cast<float4*>(buf1 + (8 * tx + w) * 32 + 4 * (ty ^ (2 * tx))) = make_float4(sc[0][w], sc[1][w], sc[2][w], sc[3][w]);
+      {
+        // ---- V of this lane's key row -> f32 in Q^T's place ([key][d], 16-byte chunk c at position c ^ (key & 7)); the
+        // TMEM region is free after this
+        uint32_t vv[32];
+        tmem_ld32_nowait(taddr + 64, vv);
+        tmem_ld_wait();
+        tc_fence_before();
+        const float* pbv = s_pb + 2 * kE + h * kDH;
+#pragma unroll
+        for (int d = 0; d < kDH; d += 4) {
+          const float4 pv = *reinterpret_cast<const float4*>(pbv + d);
+          *reinterpret_cast<float4*>(buf0 + lane * 32 + 4 * ((d >> 2) ^ (lane & 7))) =
+              make_float4(dequant1(static_cast<int>(vv[d]), a.um_v, pv.x), dequant1(static_cast<int>(vv[d + 1]), a.um_v, pv.y),
+                          dequant1(static_cast<int>(vv[d + 2]), a.um_v, pv.z), dequant1(static_cast<int>(vv[d + 3]), a.um_v, pv.w));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_free[reg]);
+
+      // ---- P V: queries 4 ty .. + 3, dims 8 tx .. + 7, one chain per output over the valid keys in order
+      float acc[4][8];
+#pragma unroll
+      for (int x = 0; x < 4; x++)
+#pragma unroll
+        for (int w = 0; w < 8; w++) acc[x][w] = 0.0f;
+#pragma unroll 4
+      for (int j = 0; j < len; j++) {
+        const float4 p4 = *reinterpret_cast<const float4*>(buf1 + j * 32 + 4 * (ty ^ (2 * (j >> 3))));
+        const float4 va = *reinterpret_cast<const float4*>(buf0 + j * 32 + 4 * ((2 * tx) ^ (j & 7)));
+        const float4 vb = *reinterpret_cast<const float4*>(buf0 + j * 32 + 4 * ((2 * tx + 1) ^ (j & 7)));
+        const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+        const float vv[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+        for (int x = 0; x < 4; x++)
+#pragma unroll
+          for (int w = 0; w < 8; w += 2) ffma2(acc[x][w], acc[x][w + 1], pv[x], pv[x], vv[w], vv[w + 1]);
+      }
+      // ---- Wo's operand: 8 bytes per (query row, thread); padded query rows carry quantize(0) like the split path
+#pragma unroll
+      for (int x = 0; x < 4; x++) {
+        const int i = 4 * ty + x;
+        if (i < T) {
+          uint2 o = make_uint2(0x7f7f7f7fu, 0x7f7f7f7fu);
+          if (i < len) {
+            o.x = pack4(quantize1(acc[x][0], a.aq_out), quantize1(acc[x][1], a.aq_out), quantize1(acc[x][2], a.aq_out),
+                        quantize1(acc[x][3], a.aq_out));
+            o.y = pack4(quantize1(acc[x][4], a.aq_out), quantize1(acc[x][5], a.aq_out), quantize1(acc[x][6], a.aq_out),
+                        quantize1(acc[x][7], a.aq_out));
+          }
+          *reinterpret_cast<uint2*>(out_base + static_cast<size_t>(i) * kE + h * kDH + 8 * tx) = o;
+        }
+      }
+      __syncwarp();  // the staging tiles are rewritten by the next unit
     }
   }
   tc_fence_before();
@@ -911,8 +938,8 @@ int launch_enc_attention(const EncAttnArgs& a, int num_sms, cudaStream_t stream)
   const bool single = variant == 1;
   if (a.T <= 32 && variant == 0) {
     const int tiles4 = (a.B + 3) / 4;
-    if (ensure_dyn_smem(enc_attention_warp_kernel, Smem::total) != cudaSuccess) return 1;
-    return launch_pdl(enc_attention_warp_kernel, dim3(tiles4 < num_sms ? tiles4 : num_sms), dim3(kThreadsEa), Smem::total, stream,
+    if (ensure_dyn_smem(enc_attention_warp_kernel, SmemW::total) != cudaSuccess) return 1;
+    return launch_pdl(enc_attention_warp_kernel, dim3(tiles4 < num_sms ? tiles4 : num_sms), dim3(kThreadsW), SmemW::total, stream,
                       a) != cudaSuccess;
   }
   if (a.T <= 32 && !single) {
