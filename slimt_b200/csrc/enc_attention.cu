@@ -604,6 +604,9 @@ __global__ void __launch_bounds__(kThreadsPair, 1) enc_attention_pair_kernel(con
 // take the CTA's (tile, head) units round-robin.  That many staging tiles only fit because they are unpadded
 // ([32][32] floats with XOR-swizzled 16-byte chunks where a padded row used to avoid the bank conflicts) and the weight
 // ring has ONE stage: the MMA of a head is ~1 k cycles of a ~9 k-cycle unit, its weights need no prefetch distance.
+// (The two FMA loops are unrolled by 2 only: twelve warps walk the unit's code at different places, and at 8 / 4 its body
+// no longer fitted the instruction cache -- ncu: no_instruction the second-largest stall, 256 vs 241 us.  Giving the four
+// query rows turns in one copy of the softmax code shrank it further but cost more in lost overlap: 259 us.)
 constexpr int kWSlots = 3;
 constexpr int kWWarps = 4 * kWSlots;
 constexpr int kThreadsW = 128 + 32 * kWWarps;
@@ -791,7 +794,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) enc_attention_warp_kernel(const 
       for (int x = 0; x < 4; x++)
 #pragma unroll
         for (int w = 0; w < 8; w++) sc[x][w] = 0.0f;
-#pragma unroll 8
+#pragma unroll 2
       for (int d = 0; d < kDH; d++) {
         const float4 q4 = *reinterpret_cast<const float4*>(buf0 + d * 32 + 4 * ty);
         const float4 ka = *reinterpret_cast<const float4*>(buf1 + d * 32 + 8 * tx);
@@ -879,7 +882,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) enc_attention_warp_kernel(const 
       for (int x = 0; x < 4; x++)
 #pragma unroll
         for (int w = 0; w < 8; w++) acc[x][w] = 0.0f;
-#pragma unroll 4
+#pragma unroll 2
       for (int j = 0; j < len; j++) {
         const float4 p4 = *reinterpret_cast<const float4*>(buf1 + j * 32 + 4 * (ty ^ (2 * (j >> 3))));
         const float4 va = *reinterpret_cast<const float4*>(buf0 + j * 32 + 4 * ((2 * tx) ^ (j & 7)));
