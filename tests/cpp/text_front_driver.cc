@@ -1,0 +1,239 @@
+// text_front_driver.cc -- ONE driver, two libraries.  The text front half of the services (Vocabulary, Splitter /
+// SentenceStream, TextProcessor, AnnotatedText, Response, combine) is driven by a line protocol on stdin; every
+// command answers with one line on stdout.
+//
+//   * compiled against include/slimt_b200_text.hh  -> tests/cpp/text_front_test   (the product's host code)
+//   * compiled with -DSLIMT_TEXT_REFERENCE against the UNMODIFIED reference sources under /root/reference (slimt/
+//     Vocabulary.cc, TextProcessor.cc, Splitter.cc, Regex.cc, Annotation.cc, Response.cc, Request.cc + the vendored
+//     sentencepiece 0.2.00)                     -> oracle/_ref/text_ref          (test infrastructure; oracle/Makefile)
+//
+// tests/golden/make_text_golden.py records the reference binary's answers; tests/test_text_front.py replays the
+// commands through the product binary and compares the answers byte for byte.
+//
+//   vocab <path>
+//   encode <hex text>                          Vocabulary::encode          -> ids | byte ranges in the text
+//   decode <id> ...                            Vocabulary::decode          -> hex text | byte ranges
+//   split <sentence|paragraph|wrapped_text> <hex prefixes or -> <hex text> SentenceStream -> sentence ranges ("-" = separator)
+//   process <mode> <wrap_length> <hex text>    TextProcessor::process      -> annotation | segments
+//   respond <mode> <wrap_length> <hex text> <ids,ids;ids,...>   Request::complete  -> source annotation | target text + annotation
+//   pivot <mode> <wrap_length> <hex text> <targets of model 1> <targets of model 2>   process(AnnotatedText&) + combine
+//   recode <mode> <wrap_length> <hex text>     AnnotatedText::to(UTF8) and back -> both offset tables
+#include <cstdio>
+#include <iostream>
+#include <memory>
+#include <optional>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#ifdef SLIMT_TEXT_REFERENCE
+#include "slimt/Aligned.hh"
+#include "slimt/Annotation.hh"
+#include "slimt/Request.hh"
+#include "slimt/Response.hh"
+#include "slimt/Splitter.hh"
+#include "slimt/TextProcessor.hh"
+#include "slimt/Types.hh"
+#include "slimt/Vocabulary.hh"
+#else
+#include "slimt_b200_text.hh"
+#endif
+
+using namespace slimt;  // NOLINT
+
+static std::string unhex(const std::string &h) {
+  if (h == "-") return "";
+  std::string out;
+  for (size_t i = 0; i + 1 < h.size(); i += 2) out.push_back(static_cast<char>(std::stoi(h.substr(i, 2), nullptr, 16)));
+  return out;
+}
+static std::string hex(std::string_view s) {
+  if (s.empty()) return "-";
+  static const char *d = "0123456789abcdef";
+  std::string out;
+  for (unsigned char c : s) out.push_back(d[c >> 4]), out.push_back(d[c & 15]);
+  return out;
+}
+static std::string range(const Range &r) { return std::to_string(r.begin) + ":" + std::to_string(r.end); }
+
+// everything the public interface of an AnnotatedText tells about its annotation
+static std::string dump(const AnnotatedText &t) {
+  std::ostringstream o;
+  o << "n=" << t.sentence_count();
+  for (size_t s = 0; s < t.sentence_count(); s++) {
+    o << " G" << hex(t.gap(s)) << " S" << range(t.sentence_as_range(s)) << " W";
+    for (size_t w = 0; w < t.word_count(s); w++) o << (w ? "," : "") << range(t.word_as_range(s, w));
+  }
+  o << " G" << hex(t.gap(t.sentence_count()));
+  return o.str();
+}
+
+static std::vector<Words> parse_targets(const std::string &spec) {
+  std::vector<Words> out;
+  if (spec == "-") return out;
+  std::stringstream all(spec);
+  std::string one;
+  while (std::getline(all, one, ';')) {
+    Words w;
+    std::stringstream ids(one);
+    std::string id;
+    while (std::getline(ids, id, ',')) w.push_back(static_cast<Word>(std::stoul(id)));
+    out.push_back(std::move(w));
+  }
+  return out;
+}
+
+// a deterministic stand-in for the decoder's attention rows: T rows over S source tokens, each summing to ~1
+static Alignment fake_alignment(size_t T, size_t S, size_t salt) {
+  Alignment a(T, Distribution(S, 0.0F));
+  for (size_t t = 0; t < T; t++) {
+    float sum = 0.0F;
+    for (size_t s = 0; s < S; s++) a[t][s] = static_cast<float>((t * 7 + s * 13 + salt) % 17 + 1), sum += a[t][s];
+    for (size_t s = 0; s < S; s++) a[t][s] /= sum;
+  }
+  return a;
+}
+
+static Histories make_histories(const Segments &segments, const std::vector<Words> &targets, size_t salt) {
+  Histories h;
+  for (size_t i = 0; i < segments.size(); i++) {
+    auto hyp = std::make_shared<Hypothesis>();
+    hyp->target = targets.at(i);
+    hyp->alignment = fake_alignment(hyp->target.size(), segments[i].size(), salt + i);
+    h.push_back(std::move(hyp));
+  }
+  return h;
+}
+
+// the Response of a request whose sentences came back as `histories`
+static Response respond(AnnotatedText &&source, Segments &&segments, const Histories &histories, const Vocabulary &vocabulary) {
+#ifdef SLIMT_TEXT_REFERENCE
+  Response out;
+  std::optional<TranslationCache> cache;
+  auto request = std::make_shared<Request>(0, 0, std::move(source), std::move(segments), vocabulary, cache,
+                                           [&out](Response &&r) {
+                                             out = std::move(r);
+                                             return nullptr;
+                                           });
+  for (size_t i = 0; i < histories.size(); i++) request->process(i, histories[i]);
+  return out;
+#else
+  (void)segments;
+  return make_response(std::move(source), histories, vocabulary);
+#endif
+}
+
+static std::unique_ptr<TextProcessor> make_processor(const std::string &mode, const Vocabulary &vocabulary) {
+#ifdef SLIMT_TEXT_REFERENCE
+  return std::make_unique<TextProcessor>(mode, vocabulary, Aligned());
+#else
+  return std::make_unique<TextProcessor>(mode, vocabulary);
+#endif
+}
+
+int main() {
+  std::unique_ptr<Vocabulary> vocabulary;
+  std::string line;
+  while (std::getline(std::cin, line)) {
+    std::stringstream in(line);
+    std::string cmd;
+    in >> cmd;
+    std::ostringstream out;
+    if (cmd == "vocab") {
+      std::string path;
+      in >> path;
+      vocabulary = std::make_unique<Vocabulary>(path);
+      out << "vocab size=" << vocabulary->size() << " eos=" << vocabulary->eos_id() << " pad=" << vocabulary->pad_id();
+    } else if (cmd == "encode") {
+      std::string h;
+      in >> h;
+      const std::string text = unhex(h);
+      auto [words, views] = vocabulary->encode(text, false);
+      out << "ids";
+      for (Word w : words) out << " " << w;
+      out << " |";
+      for (auto v : views) out << " " << (v.data() - text.data()) << ":" << (v.data() - text.data() + v.size());
+    } else if (cmd == "decode") {
+      Words words;
+      Word w;
+      while (in >> w) words.push_back(w);
+      std::string text;
+      Views views = vocabulary->decode(words, text, /*ignore_eos=*/false);
+      out << "text " << hex(text) << " |";
+      for (auto v : views) out << " " << (v.data() - text.data()) << ":" << (v.data() - text.data() + v.size());
+    } else if (cmd == "split") {
+      std::string mode, hp, ht;
+      in >> mode >> hp >> ht;
+      const std::string prefixes = unhex(hp), text = unhex(ht);
+      Splitter splitter;
+      if (!prefixes.empty()) splitter.load_from_serialized(prefixes);
+      using M = SentenceStream::splitmode;
+      const M m = mode == "sentence" ? M::OneSentencePerLine : (mode == "paragraph" ? M::OneParagraphPerLine : M::WrappedText);
+      SentenceStream stream(std::string_view(text.data(), text.size()), splitter, m);
+      std::string_view snt;
+      out << "snt";
+      while (stream >> snt) {
+        if (snt.data() == nullptr) {
+          out << " -";
+        } else {
+          out << " " << (snt.data() - text.data()) << ":" << (snt.data() - text.data() + snt.size());
+        }
+      }
+      if (!stream.error_message().empty()) out << " error";
+    } else if (cmd == "process" || cmd == "respond" || cmd == "pivot" || cmd == "recode") {
+      std::string mode, ht, spec1, spec2;
+      size_t wrap = 0;
+      in >> mode >> wrap >> ht >> spec1 >> spec2;
+      auto processor = make_processor(mode, *vocabulary);
+      auto [annotated, segments] = processor->process(unhex(ht), wrap);
+      if (cmd == "process") {
+        out << "ann " << dump(annotated) << " | seg";
+        for (const Segment &s : segments) {
+          out << " ";
+          for (size_t i = 0; i < s.size(); i++) out << (i ? "," : "") << s[i];
+        }
+      } else if (cmd == "recode") {
+        out << "bytes " << dump(annotated);
+        annotated.to(Encoding::UTF8);
+        out << " | utf8";
+        for (size_t s = 0; s < annotated.sentence_count(); s++)
+          for (size_t w = 0; w < annotated.word_count(s); w++) out << " " << range(annotated.annotation.word(s, w));
+        annotated.to(Encoding::Byte);
+        out << " | back " << dump(annotated);
+      } else {
+        Segments copy = segments;
+        const Histories h1 = make_histories(copy, parse_targets(spec1), 3);
+        Response first = respond(std::move(annotated), std::move(segments), h1, *vocabulary);
+        if (cmd == "respond") {
+          out << "src " << dump(first.source) << " | tgt " << hex(first.target.text) << " " << dump(first.target) << " | align "
+              << first.alignments.size();
+        } else {
+          auto [pivot_annotated, pivot_segments] = processor->process(first.target);
+          out << "piv " << dump(pivot_annotated) << " | seg";
+          for (const Segment &s : pivot_segments) {
+            out << " ";
+            for (size_t i = 0; i < s.size(); i++) out << (i ? "," : "") << s[i];
+          }
+          Segments copy2 = pivot_segments;
+          const Histories h2 = make_histories(copy2, parse_targets(spec2), 11);
+          Response second = respond(std::move(pivot_annotated), std::move(pivot_segments), h2, *vocabulary);
+          Response combined = combine(std::move(first), std::move(second));
+          out << " | tgt " << hex(combined.target.text) << " | align";
+          char buf[64];
+          for (const Alignment &a : combined.alignments) {
+            out << " [";
+            for (const Distribution &row : a)
+              for (float p : row) std::snprintf(buf, sizeof(buf), " %a", static_cast<double>(p)), out << buf;
+            out << " ]";
+          }
+        }
+      }
+    } else if (cmd.empty()) {
+      continue;
+    } else {
+      out << "unknown command";
+    }
+    std::cout << out.str() << "\n" << std::flush;
+  }
+  return 0;
+}
