@@ -9,11 +9,13 @@
 //   slimt::Config, slimt::Blocking, slimt::Async   slimt/Frontend.hh:21-78
 //   slimt::Options, slimt::Response, combine()     slimt/Response.hh:20-58, Response.cc:126-175
 //
-// Everything above Model::forward in the reference works on text (TextProcessor, Vocabulary, Response,
-// Annotation, HTML): those stay the reference's own code and are out of scope here, so the services below
-// take and return word ids (slimt::Words), which is what the reference hands to Model::forward too
-// (Frontend.cc:30-60).  Not meant to be included together with the reference's own headers: inside the slimt
-// tree the same C ABI is bound by the provider file shown in INTEGRATION.md.
+// The text front half above Model::forward (Vocabulary, TextProcessor, sentence splitter, AnnotatedText, Response) is
+// slimt_b200_text.hh (host only; included below).  The services therefore come at two levels: on text, with the
+// reference's own signatures (Blocking::translate(model, std::vector<std::string>, options) -> std::vector<Response>,
+// Async::translate(model, std::string, options) -> Handle), and on word ids (slimt::Sentences in, WordsResponse out),
+// which is what the reference hands to Model::forward (Frontend.cc:30-60) and what the benchmarks feed.  HTML markup
+// handling (HTML.cc) is not carried.  Not meant to be included together with the reference's own headers: inside the
+// slimt tree the same C ABI is bound by the provider file shown in INTEGRATION.md.
 //
 // Error convention: the reference asserts / aborts on shape violations (qmm/Gemmology.inl.cc:51,141,
 // Macros.hh:30-42) and throws std::runtime_error from its loaders (Io.cc:294-309); here every failure of the
@@ -42,26 +44,9 @@
 #include <unistd.h>
 
 #include "slimt_b200.h"
+#include "slimt_b200_text.hh"  // Types.hh's aliases (Word, Words, Sentences, Ptr, View, Hypothesis, ...) and the text front half
 
 namespace slimt {
-
-using Word = uint32_t;
-using Words = std::vector<Word>;
-using Sentences = std::vector<Words>;
-template <class T>
-using Ptr = std::shared_ptr<T>;
-using Distribution = std::vector<float>;
-using Alignment = std::vector<Distribution>;
-struct View {
-  void *data = nullptr;
-  size_t size = 0;
-};
-struct Hypothesis {
-  Words target;
-  Alignment alignment;
-};
-using History = Ptr<Hypothesis>;
-using Histories = std::vector<History>;
 
 namespace detail {
 inline void check(int rc, const char *what) {
@@ -265,9 +250,10 @@ class MmapFile {
 // ---------------------------------------------------------------- Model (slimt/Model.hh)
 template <class Field>
 struct Package {
-  Field model;      // marian binary v1 (model.intgemm.alphas.bin)
-  Field vocabulary; // unused on this path (word ids in, word ids out)
-  Field shortlist;  // lex.s2t.bin or empty
+  Field model;       // marian binary v1 (model.intgemm.alphas.bin)
+  Field vocabulary;  // sentencepiece model (vocab.spm); may be empty when only word ids are served
+  Field shortlist;   // lex.s2t.bin or empty
+  Field ssplit;      // sentence-splitter prefix file or empty (the reference maps it but never reads it, Model.cc:58, 69)
 };
 
 class Model {
@@ -278,8 +264,8 @@ class Model {
     size_t feed_forward_depth = 2;
     size_t num_heads = 8;
     std::string split_mode = "sentence";
-    // Vocabulary::eos_id() / pad_id() (Vocabulary.hh:22-23) of the model's sentencepiece vocabulary, which stays with
-    // the reference's text front half: the ids are all this path needs from it.
+    // Vocabulary::eos_id() / pad_id() (Vocabulary.hh:22-23).  With a vocabulary in the package they are taken from it,
+    // as in the reference; a model that serves word ids only (no vocabulary) uses the values given here.
     uint32_t eos_id = 0;
     uint32_t pad_id = 0;
   };
@@ -308,6 +294,7 @@ class Model {
     if (!p.model.empty()) m.model = io::MmapFile(p.model);
     if (!p.vocabulary.empty()) m.vocabulary = io::MmapFile(p.vocabulary);
     if (!p.shortlist.empty()) m.shortlist = io::MmapFile(p.shortlist);
+    if (!p.ssplit.empty()) m.ssplit = io::MmapFile(p.ssplit);
     return m;
   }
   static size_t next_id() {  // Model.cc:28, 53: every model of the process gets the next id (the cache key's seed)
@@ -318,10 +305,17 @@ class Model {
       : id_(next_id()), config_(config), devices_(std::move(devices)), mmap_(std::move(files)) {
     create(Package<View>{{mmap_.model.data(), mmap_.model.size()},
                          {mmap_.vocabulary.data(), mmap_.vocabulary.size()},
-                         {mmap_.shortlist.data(), mmap_.shortlist.size()}});
+                         {mmap_.shortlist.data(), mmap_.shortlist.size()},
+                         {mmap_.ssplit.data(), mmap_.ssplit.size()}});
   }
   void create(const Package<View> &package) {
     if (devices_.empty()) throw std::runtime_error("Model: at least one device is required");
+    // Model.cc:56-58: the vocabulary and, on it, the text processor (always without a prefix file, as in the reference)
+    if (package.vocabulary.data != nullptr && package.vocabulary.size > 0) {
+      vocabulary_ = std::make_unique<Vocabulary>(package.vocabulary);
+      processor_ = std::make_unique<TextProcessor>(config_.split_mode, *vocabulary_);
+      config_.eos_id = vocabulary_->eos_id(), config_.pad_id = vocabulary_->pad_id();
+    }
     slimt_b200_model_config c{static_cast<int32_t>(config_.encoder_layers), static_cast<int32_t>(config_.decoder_layers),
                               static_cast<int32_t>(config_.feed_forward_depth), static_cast<int32_t>(config_.num_heads),
                               config_.eos_id, config_.pad_id};
@@ -334,6 +328,12 @@ class Model {
     int32_t e = 0, f = 0, v = 0;
     slimt_b200_model_dims(replicas_[0], &e, &f, &v);
     vocab_ = static_cast<size_t>(v);
+    if (vocabulary_ && vocabulary_->size() > vocab_) {
+      for (slimt_b200_model *m : replicas_) slimt_b200_model_destroy(m);  // (the destructor does not run for a throwing constructor)
+      replicas_.clear();
+      throw std::runtime_error("Model: the vocabulary has " + std::to_string(vocabulary_->size()) + " pieces, the model's embedding " +
+                               std::to_string(vocab_) + " rows");
+    }
     if (package.shortlist.data != nullptr && package.shortlist.size > 0) {
       shortlist_.assign(static_cast<const char *>(package.shortlist.data),
                         static_cast<const char *>(package.shortlist.data) + package.shortlist.size);
@@ -382,6 +382,16 @@ class Model {
     return histories;
   }
   const Config &config() const { return config_; }
+  // Model.hh:59-60; a model created without a vocabulary serves word ids only
+  bool has_vocabulary() const { return vocabulary_ != nullptr; }
+  const Vocabulary &vocabulary() const {
+    if (!vocabulary_) throw std::runtime_error("Model: created without a vocabulary (Package::vocabulary is empty)");
+    return *vocabulary_;
+  }
+  const TextProcessor &processor() const {
+    if (!processor_) throw std::runtime_error("Model: created without a vocabulary (Package::vocabulary is empty)");
+    return *processor_;
+  }
   size_t id() const { return id_; }  // Model.hh:62
   size_t vocabulary_size() const { return vocab_; }
   const std::vector<int> &devices() const { return devices_; }
@@ -397,6 +407,8 @@ class Model {
   std::vector<slimt_b200_model *> replicas_;
   size_t vocab_ = 0;
   std::vector<char> shortlist_;
+  std::unique_ptr<Vocabulary> vocabulary_;
+  std::unique_ptr<TextProcessor> processor_;
 };
 
 // Model.hh:85-89, Model.cc:206-245
@@ -478,16 +490,11 @@ struct Config {
   size_t wrap_length = 128;
 };
 
-// Response.hh:45-48
-struct Options {
-  bool alignment = false;  // include alignments or not
-  bool html = false;       // text handling: not on this path, ignored
-};
-
-// Response (Response.hh:20-43) at the level this path works on: the reference's AnnotatedText source / target become
-// the sentences' word ids; alignments[i][t][s] = p(source token s | target token t) of sentence i (head 0 of the last
-// decoder layer's cross-attention, Model.cc:84-108), empty unless Options::alignment.
-struct Response {
+// Response (Response.hh:20-43) at the WORD-ID level of this path: the reference's AnnotatedText source / target are the
+// sentences' word ids here; alignments[i][t][s] = p(source token s | target token t) of sentence i (head 0 of the last
+// decoder layer's cross-attention, Model.cc:84-108), empty unless Options::alignment.  The text-level slimt::Response
+// (AnnotatedText source / target) and Options are in slimt_b200_text.hh.
+struct WordsResponse {
   Sentences source;  // one entry per SEGMENT (a sentence longer than Config::wrap_length is several, TextProcessor.cc:123)
   Sentences target;
   std::vector<Alignment> alignments;
@@ -497,11 +504,11 @@ struct Response {
   size_t size() const { return source.size(); }
 };
 
-// remap_alignments + combine (Response.cc:126-175) for pivoting.  On word ids the pivot sentence is handed to the second
+// remap_alignments + combine (Response.cc:126-175) for pivoting on word ids: the pivot sentence is handed to the second
 // model as produced, so the character-overlap transfer between two tokenisations of the pivot text is the identity and
 // what remains is the marginalisation p(s | t) = sum_q p(s | q) p(q | t).
-inline Response combine(Response &&first, Response &&second) {
-  Response out;
+inline WordsResponse combine(WordsResponse &&first, WordsResponse &&second) {
+  WordsResponse out;
   // (a pivot sentence the second service had to wrap again has no one-to-one segment any more: no combined alignment)
   if (!first.alignments.empty() && second.alignments.size() == first.alignments.size()) {
     for (size_t i = 0; i < first.source.size(); i++) {
@@ -521,25 +528,118 @@ inline Response combine(Response &&first, Response &&second) {
   return out;
 }
 
-// Blocking::translate (Frontend.cc:91-145 + exhaust() :42-60) on word ids: one Batcher, per-batch shortlist,
-// Model::forward per batch -- dealt to every replica of the model -- all inside one C-ABI call.
+// Blocking (Frontend.hh:41-57, Frontend.cc:88-205).  Both levels end in serve(): the segments of the whole call go
+// through the cache and then through ONE C-ABI call -- one Batcher, per-batch shortlist, Model::forward per batch,
+// batches dealt to every replica of the model (exhaust(), Frontend.cc:42-60).
 class Blocking {
  public:
   explicit Blocking(const Config &config) : config_(config), cache_(make_cache(config.cache_size)) {}
   // a service that shares another one's cache (Async's workers, Frontend.cc:207-210)
   Blocking(const Config &config, Ptr<TranslationCache> cache) : config_(config), cache_(std::move(cache)) {}
 
-  Response translate(const Ptr<Model> &model, const Sentences &sources, const Options &options = Options()) {
-    Response response;
+  // ---- text level: the reference's own signatures (Frontend.cc:91-145)
+  std::vector<Response> translate(const Ptr<Model> &model, std::vector<std::string> sources, const Options &options = Options()) {
+    if (options.html) throw std::runtime_error("Options::html: markup handling (HTML.cc) is not part of this path");
+    const TextProcessor &processor = model->processor();
+    // TextProcessor::process per source; independent, so spread over Config::workers host threads
+    std::vector<AnnotatedText> annotated(sources.size());
+    std::vector<Segments> segments(sources.size());
+    parallel_for(sources.size(), [&](size_t i) {
+      std::tie(annotated[i], segments[i]) = processor.process(std::move(sources[i]), config_.wrap_length);
+    });
+    return respond(model, std::move(annotated), std::move(segments), options);
+  }
+
+  // Frontend.cc:147-205: source -> pivot with `first`; the pivot TEXT is re-tokenised sentence by sentence with the
+  // second model's processor (no re-splitting, no wrapping) -> target; alignments are carried across the two
+  // tokenisations of the pivot text (remap_alignments)
+  std::vector<Response> pivot(const Ptr<Model> &first, const Ptr<Model> &second, std::vector<std::string> sources,
+                              const Options &options = Options()) {
+    std::vector<Response> source_to_pivots = translate(first, std::move(sources), options);
+    const TextProcessor &processor = second->processor();
+    std::vector<AnnotatedText> annotated(source_to_pivots.size());
+    std::vector<Segments> segments(source_to_pivots.size());
+    parallel_for(source_to_pivots.size(), [&](size_t i) {
+      std::tie(annotated[i], segments[i]) = processor.process(source_to_pivots[i].target);
+    });
+    std::vector<Response> pivot_to_targets = respond(second, std::move(annotated), std::move(segments), options);
+    std::vector<Response> responses;
+    for (size_t i = 0; i < source_to_pivots.size(); i++)
+      responses.push_back(combine(std::move(source_to_pivots[i]), std::move(pivot_to_targets[i])));
+    return responses;
+  }
+
+  // ---- word-id level
+  WordsResponse translate(const Ptr<Model> &model, const Sentences &sources, const Options &options = Options()) {
+    WordsResponse response;
     // segments (TextProcessor::process + wrap, on word ids)
     response.sentence_begin.push_back(0);
     for (const Words &s : sources) {
       wrap(s, config_.wrap_length, model->config().eos_id, response.source);
       response.sentence_begin.push_back(response.source.size());
     }
-    const Sentences &segments = response.source;
-    // cache prefill (Request.cc:58-78): a segment this model has translated before is not batched again.  A record
-    // stored by a request that did not ask for alignments cannot answer one that does.
+    const Histories histories = serve(model, response.source, options);
+    response.target.reserve(histories.size());
+    for (const History &h : histories) response.target.push_back(h->target);
+    if (options.alignment)
+      for (const History &h : histories) response.alignments.push_back(h->alignment);
+    return response;
+  }
+  // Blocking::pivot on word ids: the two models must share the pivot-language vocabulary; the pivot sentences are
+  // passed on as produced, EOS included, like the reference's segments (TextProcessor.cc:132-143).
+  WordsResponse pivot(const Ptr<Model> &first, const Ptr<Model> &second, const Sentences &sources, const Options &options = Options()) {
+    WordsResponse source_to_pivot = translate(first, sources, options);
+    WordsResponse pivot_to_target = translate(second, source_to_pivot.target, options);
+    return combine(std::move(source_to_pivot), std::move(pivot_to_target));
+  }
+  size_t cache_hits() const { return cache_hits_; }
+
+ private:
+  template <class F>
+  void parallel_for(size_t n, F &&body) const {
+    const size_t threads = std::min(n, std::max<size_t>(1, config_.workers));
+    if (threads <= 1) {
+      for (size_t i = 0; i < n; i++) body(i);
+      return;
+    }
+    std::atomic<size_t> next{0};
+    std::exception_ptr error;
+    std::mutex error_mu;
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < threads; t++)
+      pool.emplace_back([&]() {
+        try {
+          for (size_t i = next++; i < n; i = next++) body(i);
+        } catch (...) {
+          std::lock_guard<std::mutex> lock(error_mu);
+          if (!error) error = std::current_exception();
+        }
+      });
+    for (std::thread &t : pool) t.join();
+    if (error) std::rethrow_exception(error);
+  }
+
+  // all segments of all requests of a call in one pool -> serve() -> one Response per request (Request::complete)
+  std::vector<Response> respond(const Ptr<Model> &model, std::vector<AnnotatedText> &&annotated, std::vector<Segments> &&segments,
+                                const Options &options) {
+    Sentences pool;
+    for (const Segments &s : segments) pool.insert(pool.end(), s.begin(), s.end());
+    // the decoded text needs every history's alignment only when asked for; the words always
+    const Histories histories = serve(model, pool, options);
+    std::vector<Response> responses(annotated.size());
+    size_t at = 0;
+    for (size_t i = 0; i < annotated.size(); i++) {
+      Histories mine(histories.begin() + at, histories.begin() + at + segments[i].size());
+      at += segments[i].size();
+      responses[i] = make_response(std::move(annotated[i]), mine, model->vocabulary());
+      if (!options.alignment) responses[i].alignments.clear();
+    }
+    return responses;
+  }
+
+  // cache prefill (Request.cc:58-78): a segment this model has translated before is not batched again.  A record
+  // stored by a request that did not ask for alignments cannot answer one that does.  The rest: run().
+  Histories serve(const Ptr<Model> &model, const Sentences &segments, const Options &options) {
     Histories histories(segments.size());
     std::vector<size_t> todo;
     for (size_t i = 0; i < segments.size(); i++) {
@@ -556,15 +656,9 @@ class Blocking {
     if (!todo.empty()) run(model, segments, todo, options, histories);
     for (size_t i : todo)
       if (cache_) cache_->store(cache_key(model->id(), segments[i]), histories[i]);  // Request.cc:120-125
-    response.target.reserve(segments.size());
-    for (const History &h : histories) response.target.push_back(h->target);
-    if (options.alignment)
-      for (const History &h : histories) response.alignments.push_back(h->alignment);
-    return response;
+    return histories;
   }
-  size_t cache_hits() const { return cache_hits_; }
 
- private:
   // Frontend.cc:91-145 + exhaust() :42-60 for the segments listed in `todo`: one Batcher, per-batch shortlist,
   // Model::forward per batch -- dealt to every replica of the model -- all inside one C-ABI call.
   void run(const Ptr<Model> &model, const Sentences &segments, const std::vector<size_t> &todo, const Options &options,
@@ -608,27 +702,24 @@ class Blocking {
     }
   }
 
- public:
-  // Blocking::pivot (Frontend.cc:147-205) on word ids: source -> pivot with `first`, pivot -> target with `second`.
-  // The reference detokenises the pivot text and re-tokenises it with the second model's TextProcessor (text
-  // handling: out of scope here), so at this level the two models must share the pivot-language vocabulary; the
-  // pivot sentences are passed on as produced, EOS included, like the reference's segments (TextProcessor.cc:132-143).
-  Response pivot(const Ptr<Model> &first, const Ptr<Model> &second, const Sentences &sources,
-                 const Options &options = Options()) {
-    Response source_to_pivot = translate(first, sources, options);
-    Response pivot_to_target = translate(second, source_to_pivot.target, options);
-    return combine(std::move(source_to_pivot), std::move(pivot_to_target));
-  }
-
- private:
   Config config_;
   Ptr<TranslationCache> cache_;
   size_t cache_hits_ = 0;
 };
 
-// Async (Frontend.cc:207-323): `workers` threads take requests from one queue and answer through futures.  A request
-// is served by Blocking's path, i.e. its batches are dealt to every GPU replica of its model; requests in flight at
-// the same time share the replicas (each device context serialises the batches it is given).
+// Handle (Response.hh:60-91): what Async returns for a text request -- the future of its Response
+class Handle {
+ public:
+  explicit Handle(std::future<Response> &&future) : future_(std::move(future)) {}
+  std::future<Response> &future() { return future_; }
+
+ private:
+  std::future<Response> future_;
+};
+
+// Async (Frontend.hh:59-78, Frontend.cc:207-323): `workers` threads take requests from one queue and answer through
+// futures.  A request is served by Blocking's path, i.e. its batches are dealt to every GPU replica of its model;
+// requests in flight at the same time share the replicas (each device context serialises the batches it is given).
 class Async {
  public:
   explicit Async(const Config &config) : config_(config), cache_(make_cache(config.cache_size)) {
@@ -642,13 +733,33 @@ class Async {
     cv_.notify_all();
     for (std::thread &t : workers_) t.join();
   }
-  std::future<Response> translate(const Ptr<Model> &model, Sentences sources, const Options &options = Options()) {
-    return enqueue(Job{model, nullptr, std::move(sources), options, {}});
+  // ---- text level (Frontend.cc:229-314)
+  Handle translate(const Ptr<Model> &model, std::string source, const Options &options = Options()) {
+    Job job{model, nullptr, {}, options, {}, true, std::move(source), {}};
+    Handle handle(job.text_promise.get_future());
+    enqueue(std::move(job));
+    return handle;
+  }
+  Handle pivot(const Ptr<Model> &first, const Ptr<Model> &second, std::string source, const Options &options = Options()) {
+    Job job{first, second, {}, options, {}, true, std::move(source), {}};
+    Handle handle(job.text_promise.get_future());
+    enqueue(std::move(job));
+    return handle;
+  }
+  // ---- word-id level
+  std::future<WordsResponse> translate(const Ptr<Model> &model, Sentences sources, const Options &options = Options()) {
+    Job job{model, nullptr, std::move(sources), options, {}, false, {}, {}};
+    std::future<WordsResponse> f = job.promise.get_future();
+    enqueue(std::move(job));
+    return f;
   }
   // Async::pivot (Frontend.cc:259-314): the second translation is chained behind the first inside the worker
-  std::future<Response> pivot(const Ptr<Model> &first, const Ptr<Model> &second, Sentences sources,
-                              const Options &options = Options()) {
-    return enqueue(Job{first, second, std::move(sources), options, {}});
+  std::future<WordsResponse> pivot(const Ptr<Model> &first, const Ptr<Model> &second, Sentences sources,
+                                   const Options &options = Options()) {
+    Job job{first, second, std::move(sources), options, {}, false, {}, {}};
+    std::future<WordsResponse> f = job.promise.get_future();
+    enqueue(std::move(job));
+    return f;
   }
 
  private:
@@ -656,19 +767,22 @@ class Async {
     Ptr<Model> first, second;
     Sentences sources;
     Options options;
-    std::promise<Response> promise;
+    std::promise<WordsResponse> promise;
+    bool is_text = false;
+    std::string text;
+    std::promise<Response> text_promise;
   };
-  std::future<Response> enqueue(Job job) {
-    std::future<Response> f = job.promise.get_future();
+  void enqueue(Job job) {
     {
       std::lock_guard<std::mutex> lock(mu_);
       queue_.push_back(std::move(job));
     }
     cv_.notify_one();
-    return f;
   }
   void work() {
-    Blocking service(config_, cache_);  // one cache for the whole service (Frontend.cc:207-210)
+    Config one = config_;
+    one.workers = 1;  // (a request's own tokenisation stays on the worker that serves it)
+    Blocking service(one, cache_);  // one cache for the whole service (Frontend.cc:207-210)
     for (;;) {
       Job job;
       {
@@ -679,10 +793,21 @@ class Async {
         queue_.pop_front();
       }
       try {
-        job.promise.set_value(job.second ? service.pivot(job.first, job.second, job.sources, job.options)
-                                         : service.translate(job.first, job.sources, job.options));
+        if (job.is_text) {
+          std::vector<std::string> sources(1, std::move(job.text));
+          std::vector<Response> r = job.second ? service.pivot(job.first, job.second, std::move(sources), job.options)
+                                               : service.translate(job.first, std::move(sources), job.options);
+          job.text_promise.set_value(std::move(r[0]));
+        } else {
+          job.promise.set_value(job.second ? service.pivot(job.first, job.second, job.sources, job.options)
+                                           : service.translate(job.first, job.sources, job.options));
+        }
       } catch (...) {
-        job.promise.set_exception(std::current_exception());
+        if (job.is_text) {
+          job.text_promise.set_exception(std::current_exception());
+        } else {
+          job.promise.set_exception(std::current_exception());
+        }
       }
     }
   }

@@ -1248,9 +1248,14 @@ inline Alignment transfer_through_characters(const std::vector<Range> &source_si
       continue;
     }
     const size_t left = std::max(q.begin, s.begin), right = std::min(q.end, s.end);
-    const size_t shared = right - left, spread = q.size();
+    // The reference asserts left < right here (Response.cc:49) and, built without assertions, goes on with a wrapped
+    // difference.  The case is real -- a piece that decodes to nothing (a lone U+2581 at the start of the pivot
+    // sentence) facing a non-empty token of the other tokenisation -- so instead: no shared characters, no mass moved;
+    // a zero-width token of the second tokenisation hands its whole mass to the token it falls into.
+    const size_t shared = right > left ? right - left : 0, spread = q.size();
     for (size_t t = 0; t < pivot_given_targets.size(); t++)
-      remapped[t][sq] += static_cast<float>(shared) * pivot_given_targets[t][qt] / static_cast<float>(spread);
+      remapped[t][sq] += spread == 0 ? pivot_given_targets[t][qt]
+                                     : static_cast<float>(shared) * pivot_given_targets[t][qt] / static_cast<float>(spread);
     if (s.end == q.end) {
       sq++, qt++;
     } else if (s.end > q.end) {

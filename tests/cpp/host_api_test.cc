@@ -88,11 +88,11 @@ int main(int argc, char **argv) {
     slimt::Config config;
     config.max_words = 96;
     slimt::Blocking blocking(config);
-    slimt::Response plain = blocking.translate(model, sources);
+    slimt::WordsResponse plain = blocking.translate(model, sources);
     put_sentences(out, plain.target);
     slimt::Options with_alignment;
     with_alignment.alignment = true;
-    slimt::Response aligned = blocking.translate(model, sources, with_alignment);
+    slimt::WordsResponse aligned = blocking.translate(model, sources, with_alignment);
     if (aligned.target != plain.target || aligned.alignments.size() != sources.size()) throw std::runtime_error("alignment run differs");
     for (size_t i = 0; i < sources.size(); i++) {
       uint32_t rows = aligned.alignments[i].size();
@@ -109,13 +109,13 @@ int main(int argc, char **argv) {
       auto two = std::make_shared<slimt::Model>(slimt::preset::tiny(), paths, std::vector<int>{0, 0});
       config.workers = 2;
       slimt::Async async(config);
-      std::future<slimt::Response> f1 = async.translate(two, sources);
-      std::future<slimt::Response> f2 = async.translate(two, slimt::Sentences(sources.begin(), sources.begin() + 1));
-      std::future<slimt::Response> f3 = async.pivot(two, model, sources, with_alignment);
-      std::future<slimt::Response> f4 = async.translate(model, sources);  // a second model on the same device, concurrently
+      std::future<slimt::WordsResponse> f1 = async.translate(two, sources);
+      std::future<slimt::WordsResponse> f2 = async.translate(two, slimt::Sentences(sources.begin(), sources.begin() + 1));
+      std::future<slimt::WordsResponse> f3 = async.pivot(two, model, sources, with_alignment);
+      std::future<slimt::WordsResponse> f4 = async.translate(model, sources);  // a second model on the same device, concurrently
       put_sentences(out, f1.get().target);
       put_sentences(out, f2.get().target);
-      slimt::Response pivoted = f3.get();
+      slimt::WordsResponse pivoted = f3.get();
       put_sentences(out, pivoted.target);
       if (pivoted.alignments.size() != sources.size()) throw std::runtime_error("pivot alignments missing");
       for (size_t i = 0; i < sources.size(); i++) {
@@ -131,7 +131,7 @@ int main(int argc, char **argv) {
       wrapped.workers = 1;
       wrapped.wrap_length = 6;
       slimt::Blocking service(wrapped);
-      slimt::Response first = service.translate(model, sources, with_alignment);
+      slimt::WordsResponse first = service.translate(model, sources, with_alignment);
       if (first.sentence_begin.size() != sources.size() + 1 || first.sentence_begin.back() != first.source.size())
         throw std::runtime_error("wrap: sentence map");
       if (first.source.size() <= sources.size()) throw std::runtime_error("wrap: nothing was wrapped");
@@ -148,21 +148,21 @@ int main(int argc, char **argv) {
       }
       if (service.cache_hits() != 0) throw std::runtime_error("cache: hit on first sight");
       // the same request again: every segment comes from the cache, identical histories
-      slimt::Response again = service.translate(model, sources, with_alignment);
+      slimt::WordsResponse again = service.translate(model, sources, with_alignment);
       if (service.cache_hits() != first.source.size()) throw std::runtime_error("cache: expected every segment to hit");
       if (again.target != first.target || again.alignments != first.alignments) throw std::runtime_error("cache: different answer");
       // the segments translated directly by a service without a cache (same batches as the first pass)
       slimt::Config plain_config = wrapped;
       plain_config.cache_size = 0;
       slimt::Blocking no_cache(plain_config);
-      slimt::Response direct = no_cache.translate(model, first.source, with_alignment);
+      slimt::WordsResponse direct = no_cache.translate(model, first.source, with_alignment);
       if (direct.target != first.target || direct.alignments != first.alignments) throw std::runtime_error("wrap: segments differ");
       if (no_cache.cache_hits() != 0) throw std::runtime_error("cache: disabled cache hit");
       // another model does not see this model's records
       auto other = std::make_shared<slimt::Model>(slimt::preset::tiny(), paths);
       if (other->id() == model->id()) throw std::runtime_error("model ids");
       const size_t before = service.cache_hits();
-      slimt::Response other_response = service.translate(other, sources, with_alignment);
+      slimt::WordsResponse other_response = service.translate(other, sources, with_alignment);
       if (service.cache_hits() != before || other_response.target != first.target) throw std::runtime_error("cache: model id not in the key");
     }
     std::printf("host_api_test ok\n");
