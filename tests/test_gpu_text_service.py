@@ -138,5 +138,8 @@ def test_text_in_text_out(gpu_ctx, tmp_path, wrap_length, use_shortlist):
         for s, row in enumerate(rows):
             m = row.reshape(-1, n_src[s])
             assert np.allclose(m.sum(axis=1), 1.0, atol=1e-3)
-    assert [l.split(" ", 1)[1] for l in lines if l.startswith("apivot ")] == [l.split(" ", 1)[1] for l in pivot[:3]]
+    apivot = [l.split(" ", 1)[1] for l in lines if l.startswith("apivot ")]
+    assert len(apivot) == 3 and apivot[0] == pivot[0].split(" ", 1)[1]
+    if not use_shortlist:  # (with a shortlist the candidate set is the union over the BATCH, Model.cc:116-120: one text alone
+        assert apivot == [l.split(" ", 1)[1] for l in pivot[:3]]  # and three texts pooled may legitimately decode differently)
     assert lines[-1] == "html refused"
