@@ -779,38 +779,96 @@ class Async {
     }
     cv_.notify_one();
   }
+  // AggregateBatcher (Batcher.hh:128-200): requests that wait at the same time are batched TOGETHER.  A worker that
+  // wakes up takes the oldest request and every queued request of the same kind (same model, same level, same
+  // options, not a pivot) and serves them in one service call, so a burst of single-sentence requests fills GPU-sized
+  // batches instead of running one tiny batch each.  As in the reference, what a shortlisted model answers may then
+  // depend on who shared the batch (the candidate set is the union over the batch, Model.cc:116-120).
+  static bool poolable(const Job &a, const Job &b) {
+    return !a.second && !b.second && a.first == b.first && a.is_text == b.is_text && a.options.alignment == b.options.alignment &&
+           a.options.html == b.options.html;
+  }
   void work() {
     Config one = config_;
     one.workers = 1;  // (a request's own tokenisation stays on the worker that serves it)
     Blocking service(one, cache_);  // one cache for the whole service (Frontend.cc:207-210)
     for (;;) {
-      Job job;
+      std::vector<Job> jobs;
       {
         std::unique_lock<std::mutex> lock(mu_);
         cv_.wait(lock, [this]() { return shutdown_ || !queue_.empty(); });
         if (queue_.empty()) return;
-        job = std::move(queue_.front());
+        jobs.push_back(std::move(queue_.front()));
         queue_.pop_front();
+        for (auto it = queue_.begin(); it != queue_.end();) {
+          if (poolable(jobs.front(), *it)) {
+            jobs.push_back(std::move(*it));
+            it = queue_.erase(it);
+          } else {
+            ++it;
+          }
+        }
       }
+      service_calls_++;
+      requests_served_ += jobs.size();
       try {
-        if (job.is_text) {
-          std::vector<std::string> sources(1, std::move(job.text));
-          std::vector<Response> r = job.second ? service.pivot(job.first, job.second, std::move(sources), job.options)
-                                               : service.translate(job.first, std::move(sources), job.options);
-          job.text_promise.set_value(std::move(r[0]));
+        Job &head = jobs.front();
+        if (head.is_text) {
+          if (head.second) {
+            std::vector<Response> r = service.pivot(head.first, head.second, std::vector<std::string>(1, std::move(head.text)), head.options);
+            head.text_promise.set_value(std::move(r[0]));
+          } else {
+            std::vector<std::string> sources;
+            for (Job &j : jobs) sources.push_back(std::move(j.text));
+            std::vector<Response> r = service.translate(head.first, std::move(sources), head.options);
+            for (size_t k = 0; k < jobs.size(); k++) jobs[k].text_promise.set_value(std::move(r[k]));
+          }
+        } else if (head.second) {
+          head.promise.set_value(service.pivot(head.first, head.second, head.sources, head.options));
+        } else if (jobs.size() == 1) {
+          head.promise.set_value(service.translate(head.first, head.sources, head.options));
         } else {
-          job.promise.set_value(job.second ? service.pivot(job.first, job.second, job.sources, job.options)
-                                           : service.translate(job.first, job.sources, job.options));
+          Sentences pooled;
+          std::vector<size_t> first_sentence(1, 0);
+          for (const Job &j : jobs) {
+            pooled.insert(pooled.end(), j.sources.begin(), j.sources.end());
+            first_sentence.push_back(pooled.size());
+          }
+          WordsResponse all = service.translate(head.first, pooled, head.options);
+          for (size_t k = 0; k < jobs.size(); k++) {  // every request gets the segments of its own sentences back
+            WordsResponse mine;
+            const size_t s0 = first_sentence[k], s1 = first_sentence[k + 1];
+            const size_t g0 = all.sentence_begin[s0], g1 = all.sentence_begin[s1];
+            mine.source.assign(all.source.begin() + g0, all.source.begin() + g1);
+            mine.target.assign(all.target.begin() + g0, all.target.begin() + g1);
+            if (!all.alignments.empty()) mine.alignments.assign(all.alignments.begin() + g0, all.alignments.begin() + g1);
+            for (size_t s = s0; s <= s1; s++) mine.sentence_begin.push_back(all.sentence_begin[s] - g0);
+            jobs[k].promise.set_value(std::move(mine));
+          }
         }
       } catch (...) {
-        if (job.is_text) {
-          job.text_promise.set_exception(std::current_exception());
-        } else {
-          job.promise.set_exception(std::current_exception());
+        // a promise that was already answered keeps its answer; the others carry the error
+        for (Job &j : jobs) {
+          try {
+            if (j.is_text) {
+              j.text_promise.set_exception(std::current_exception());
+            } else {
+              j.promise.set_exception(std::current_exception());
+            }
+          } catch (const std::future_error &) {
+          }
         }
       }
     }
   }
+
+ public:
+  // monitoring: service calls made so far and requests they answered (requests / calls > 1: requests were pooled)
+  size_t service_calls() const { return service_calls_; }
+  size_t requests_served() const { return requests_served_; }
+
+ private:
+  std::atomic<size_t> service_calls_{0}, requests_served_{0};
   Config config_;
   Ptr<TranslationCache> cache_;
   std::vector<std::thread> workers_;

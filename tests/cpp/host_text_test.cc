@@ -97,6 +97,41 @@ int main(int argc, char **argv) {
     print("cached", a2);
     Handle h3 = async.pivot(model, model, sources[0], options);
     print("apivot", h3.future().get());
+    // a burst of single-line requests: the requests that queue up while the first is served share one service call
+    // (AggregateBatcher, Batcher.hh:128-200); each answer is compared with the same text served alone
+    {
+      std::vector<std::string> burst;
+      for (const std::string &s : sources) {
+        std::stringstream all(s);
+        std::string line;
+        while (std::getline(all, line, '\n'))
+          if (!line.empty()) burst.push_back(line);
+      }
+      const size_t base = burst.size();
+      for (size_t k = 0; burst.size() < 24; k++) burst.push_back(burst[k % base] + " " + burst[(k + 1) % base]);
+      Config no_cache = config;
+      no_cache.workers = 1;
+      Async pooled(no_cache);
+      std::vector<Handle> handles;
+      for (const std::string &b : burst) handles.push_back(pooled.translate(model, b, options));
+      size_t equal = 0;
+      Blocking alone(no_cache);
+      for (size_t k = 0; k < burst.size(); k++) {
+        Response got = handles[k].future().get();
+        Response want = std::move(alone.translate(model, std::vector<std::string>(1, burst[k]), options)[0]);
+        // a sentence that never produces EOS is cut at limit_factor x the BATCH's longest sentence (Model.cc:139-143), so
+        // alone it may be cut earlier than in company: the shorter answer must be the beginning of the longer
+        const std::string &a = got.target.text, &b = want.target.text;
+        const bool same_text = a.size() <= b.size() ? b.compare(0, a.size(), a) == 0 : a.compare(0, b.size(), b) == 0;
+        bool same_rows = got.alignments.size() == want.alignments.size();
+        for (size_t q = 0; same_rows && q < got.alignments.size(); q++) {
+          const size_t rows = std::min(got.alignments[q].size(), want.alignments[q].size());
+          for (size_t t = 0; t < rows; t++) same_rows = same_rows && got.alignments[q][t] == want.alignments[q][t];
+        }
+        equal += same_text && same_rows;
+      }
+      std::cout << "burst requests=" << pooled.requests_served() << " calls=" << pooled.service_calls() << " equal=" << equal << "\n";
+    }
     bool refused = false;
     try {
       Options html;

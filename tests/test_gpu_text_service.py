@@ -142,4 +142,10 @@ def test_text_in_text_out(gpu_ctx, tmp_path, wrap_length, use_shortlist):
     assert len(apivot) == 3 and apivot[0] == pivot[0].split(" ", 1)[1]
     if not use_shortlist:  # (with a shortlist the candidate set is the union over the BATCH, Model.cc:116-120: one text alone
         assert apivot == [l.split(" ", 1)[1] for l in pivot[:3]]  # and three texts pooled may legitimately decode differently)
+    # 7. a burst of 24 single-line requests through Async: pooled into fewer service calls; without a shortlist every
+    # answer equals the same text served alone (batch composition does not matter then)
+    burst = dict(kv.split("=") for kv in next(l for l in lines if l.startswith("burst ")).split()[1:])
+    assert int(burst["requests"]) == 24 and int(burst["calls"]) < 24
+    if not use_shortlist:
+        assert int(burst["equal"]) == 24
     assert lines[-1] == "html refused"
