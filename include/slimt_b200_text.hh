@@ -199,10 +199,13 @@ class ByteTrie {
       int k = first_[n];
       for (const auto &[c, to] : kids[n]) label_[k] = c, child_[k] = to, k++;
     }
+    root_.fill(-1);  // the root has the most children and is visited once per character: a direct table
+    for (const auto &[c, to] : kids[0]) root_[c] = to;
   }
   bool empty() const { return value_.size() <= 1; }
   // one step from `node` along byte c: the child or -1
   int step(int node, uint8_t c) const {
+    if (node == 0) return root_[c];
     const uint8_t *lo = label_.data() + first_[node], *hi = label_.data() + first_[node + 1];
     const uint8_t *it = std::lower_bound(lo, hi, c);
     return (it != hi && *it == c) ? child_[it - label_.data()] : -1;
@@ -223,6 +226,7 @@ class ByteTrie {
  private:
   std::vector<int> first_, child_, value_;
   std::vector<uint8_t> label_;
+  std::array<int, 256> root_{};
 };
 
 // The slice of sentencepiece::SentencePieceProcessor that slimt::Vocabulary calls (Vocabulary.cc:24-104): Load /
@@ -409,11 +413,42 @@ class Processor {
   // model's Encode, PopulateSentencePieceText (:542-631: offsets mapped back to the input, runs of unknown pieces
   // merged, byte fallback).
   std::vector<Span> encode(std::string_view input) const {
-    std::string normalized;
-    std::vector<size_t> n2o;
-    normalize(input, &normalized, &n2o);
-    const auto result = encode_unigram(normalized);
     std::vector<Span> out;
+    encode_walk(input, [&](int id, std::string_view w, size_t ob, size_t oe, bool merge, bool has_surface) {
+      const std::string_view surface = has_surface ? input.substr(ob, oe - ob) : std::string_view();
+      if (merge) {
+        Span &s = out.back();
+        s.piece.append(w), s.surface.append(surface), s.end = oe;
+      } else {
+        Span s;
+        s.id = id, s.piece.assign(w), s.surface.assign(surface), s.begin = ob, s.end = oe;
+        out.push_back(std::move(s));
+      }
+    });
+    return out;
+  }
+  // the same walk for callers that only want what slimt::Vocabulary keeps: the ids and each piece's byte range
+  void encode(std::string_view input, std::vector<uint32_t> *ids, std::vector<std::pair<size_t, size_t>> *ranges) const {
+    ids->clear(), ranges->clear();
+    encode_walk(input, [&](int id, std::string_view, size_t ob, size_t oe, bool merge, bool) {
+      if (merge) {
+        ranges->back().second = oe;
+      } else {
+        ids->push_back(static_cast<uint32_t>(id)), ranges->emplace_back(ob, oe);
+      }
+    });
+  }
+
+ private:
+  // PopulateSentencePieceText (sentencepiece_processor.cc:542-631) as a walk: emit(id, piece, begin, end, merge, has_surface)
+  // once per output piece; merge = a run of unknown pieces continues (the previous piece grows, no new one)
+  template <class Emit>
+  void encode_walk(std::string_view input, Emit &&emit) const {
+    thread_local std::string normalized;
+    thread_local std::vector<size_t> n2o;
+    thread_local std::vector<std::pair<std::string_view, int>> result;
+    normalize(input, &normalized, &n2o);
+    encode_unigram(normalized, &result);
     size_t consumed = 0;
     bool prev_unk = false;
     for (const auto &[w, id] : result) {
@@ -422,54 +457,57 @@ class Processor {
       if (end >= n2o.size()) throw std::runtime_error("sentencepiece: piece outside the normalized text");
       const size_t ob = n2o[begin], oe = n2o[end];
       if (ob > input.size() || oe > input.size() || ob > oe) throw std::runtime_error("sentencepiece: inconsistent offsets");
-      const std::string_view surface = input.substr(ob, oe - ob);
       if (unk && byte_fallback_) {
         for (size_t i = 0; i < w.size(); i++) {
-          Span s;
-          s.piece = byte_to_piece(static_cast<uint8_t>(w[i]));
-          s.id = piece_to_id(s.piece);
-          s.begin = ob, s.end = ob;
-          if (i + 1 == w.size()) s.surface.assign(surface), s.end = oe;
-          out.push_back(std::move(s));
+          const std::string piece = byte_to_piece(static_cast<uint8_t>(w[i]));
+          const bool last = i + 1 == w.size();
+          emit(piece_to_id(piece), std::string_view(piece), ob, last ? oe : ob, false, last);
         }
-      } else if (prev_unk && unk) {
-        Span &s = out.back();
-        s.piece.append(w), s.surface.append(surface), s.end = oe;
       } else {
-        Span s;
-        s.id = id, s.piece.assign(w), s.surface.assign(surface), s.begin = ob, s.end = oe;
-        out.push_back(std::move(s));
+        emit(id, w, ob, oe, prev_unk && unk, true);
       }
       consumed += w.size();
       prev_unk = unk;
     }
     if (consumed != normalized.size()) throw std::runtime_error("sentencepiece: all normalized characters are not consumed");
-    return out;
   }
+
+ public:
 
   // SentencePieceProcessor::Decode(ids, SentencePieceText*) (sentencepiece_processor.cc:754-917).  Returns false for an id
   // outside the vocabulary (the library returns an OUT_OF_RANGE status and leaves the text empty).
   bool decode(const std::vector<int> &ids, std::string *text, std::vector<Span> *spans) const {
-    text->clear(), spans->clear();
-    for (int id : ids)
-      if (!in_range(id)) return false;
-    static constexpr std::string_view kSpace = "\xe2\x96\x81";
-    for (int id : ids) {
+    std::vector<std::pair<size_t, size_t>> ranges;
+    spans->clear();
+    if (!decode(ids, text, &ranges)) return false;
+    for (size_t i = 0; i < ids.size(); i++) {
       Span s;
-      s.piece = pieces_[id].piece;
-      s.id = piece_to_id(s.piece);
+      s.id = ids[i], s.piece = pieces_[ids[i]].piece, s.begin = ranges[i].first, s.end = ranges[i].second;
+      s.surface = text->substr(s.begin, s.end - s.begin);
       spans->push_back(std::move(s));
     }
+    return true;
+  }
+  // the text and, per id, the byte range of its surface in it.  (Decode goes id -> piece -> id; pieces are unique --
+  // checked at load -- so the round trip is the identity and is not made.)
+  template <class Id>
+  bool decode(const std::vector<Id> &ids, std::string *text, std::vector<std::pair<size_t, size_t>> *ranges) const {
+    text->clear();
+    ranges->assign(ids.size(), {0, 0});
+    for (Id id : ids)
+      if (!in_range(static_cast<int>(id))) {
+        ranges->clear();
+        return false;
+      }
+    static constexpr std::string_view kSpace = "\xe2\x96\x81";
     auto set_surface = [&](size_t i, std::string_view surface) {
-      Span &s = (*spans)[i];
-      s.surface.assign(surface);
-      s.begin = text->size(), s.end = text->size() + surface.size();
+      (*ranges)[i] = {text->size(), text->size() + surface.size()};
       text->append(surface);
     };
-    auto byte_run = [&](size_t from, size_t to) {
+    auto byte_run = [&](size_t from, size_t to) {  // a run of byte pieces: one surface per UTF-8 character, on its last byte
       if (from >= to) return;
       std::string bytes;
-      for (size_t i = from; i < to; i++) bytes.push_back(static_cast<char>(piece_to_byte((*spans)[i].piece)));
+      for (size_t i = from; i < to; i++) bytes.push_back(static_cast<char>(piece_to_byte(pieces_[ids[i]].piece)));
       size_t offset = 0;
       while (offset < bytes.size()) {
         size_t used = 0;
@@ -485,36 +523,36 @@ class Processor {
     };
     size_t byte_start = 0;
     bool is_bos_ws = true, bos_ws_seen = false;
-    for (size_t i = 0; i < spans->size(); i++) {
-      const Span &s = (*spans)[i];
-      if (is_byte(s.id)) continue;
+    for (size_t i = 0; i < ids.size(); i++) {
+      const Piece &p = pieces_[ids[i]];
+      if (p.type == BYTE) continue;
       byte_run(byte_start, i);
       if (bos_ws_seen || !text->empty()) is_bos_ws = false;
       byte_start = i + 1;
-      std::string decoded;
       bos_ws_seen = false;
-      if (is_control(s.id)) {
+      const size_t begin = text->size();
+      if (p.type == CONTROL) {
         // invisible
-      } else if (is_unknown(s.id)) {
-        decoded = pieces_[s.id].piece == s.piece ? unk_surface_ : s.piece;
+      } else if (p.type == UNKNOWN) {
+        text->append(unk_surface_);
       } else {
-        std::string_view piece = s.piece;
+        std::string_view piece = p.piece;
         if (is_bos_ws && (add_dummy_prefix_ || remove_extra_whitespaces_)) {
           if (piece.substr(0, kSpace.size()) == kSpace) piece.remove_prefix(kSpace.size()), bos_ws_seen = true;
           if (remove_extra_whitespaces_) bos_ws_seen = false;
         }
         for (size_t k = 0; k < piece.size();) {
-          if (piece.compare(k, kSpace.size(), kSpace) == 0) {
-            decoded.push_back(' ');
+          if (piece[k] == kSpace[0] && piece.compare(k, kSpace.size(), kSpace) == 0) {
+            text->push_back(' ');
             k += kSpace.size();
           } else {
-            decoded.push_back(piece[k++]);
+            text->push_back(piece[k++]);
           }
         }
       }
-      set_surface(i, decoded);
+      (*ranges)[i] = {begin, text->size()};
     }
-    byte_run(byte_start, spans->size());
+    byte_run(byte_start, ids.size());
     return true;
   }
 
@@ -562,6 +600,8 @@ class Processor {
       throw std::runtime_error("sentencepiece model: byte_fallback without 256 byte pieces");
     trie_.build(normal);
     user_.build(user);
+    score_.clear(), type_.clear();
+    for (const Piece &p : pieces_) score_.push_back(p.score), type_.push_back(static_cast<uint8_t>(p.type));
     // precompiled_charsmap = u32 size of the trie blob, the Darts double array (u32 units), the replacement strings
     // (NUL-terminated, indexed by the trie's values)  (normalizer.cc:275-309)
     if (!charsmap_.empty()) {
@@ -628,17 +668,20 @@ class Processor {
   // unknown character costs min_score - 10; a user-defined piece scores length * max_score - 0.1; the first of
   // equally good paths is kept (strict >).  The arithmetic types follow the library's (float scores, the candidate sum
   // formed in double when a user-defined piece is involved, stored back as float).
-  std::vector<std::pair<std::string_view, int>> encode_unigram(std::string_view normalized) const {
-    std::vector<std::pair<std::string_view, int>> results;
-    if (normalized.empty()) return results;
-    struct Node {
-      int id = -1;
-      float score = 0.0F;
-      int starts_at = -1;
-    };
+  struct ViterbiNode {
+    int id = -1;
+    float score = 0.0F;
+    int starts_at = -1;
+  };
+  void encode_unigram(std::string_view normalized, std::vector<std::pair<std::string_view, int>> *out) const {
+    std::vector<std::pair<std::string_view, int>> &results = *out;
+    results.clear();
+    if (normalized.empty()) return;
+    using Node = ViterbiNode;
     const int size = static_cast<int>(normalized.size());
     const float unk_score = min_score_ - 10.0F;
-    std::vector<Node> best(static_cast<size_t>(size) + 1);
+    thread_local std::vector<Node> best;
+    best.assign(static_cast<size_t>(size) + 1, Node());
     int starts_at = 0;
     while (starts_at < size) {
       const float till_here = best[starts_at].score;
@@ -651,18 +694,19 @@ class Processor {
         if (node < 0) break;
         const int ret = trie_.value(node);
         if (ret < 0) continue;
-        if (pieces_[ret].type == UNUSED) continue;
+        const uint8_t type = type_[ret];
+        if (type == UNUSED) continue;
         Node &target = best[key_pos];
         const size_t length = static_cast<size_t>(key_pos - starts_at);
         bool better;
         float stored;
-        if (pieces_[ret].type == USER_DEFINED) {
+        if (type == USER_DEFINED) {
           const double cand = (static_cast<float>(length) * max_score_ - 0.1) + static_cast<double>(till_here);
           better = target.starts_at == -1 || cand > static_cast<double>(target.score);
           stored = static_cast<float>(cand);
         } else {
           // GetScoreInlined is a float, but the ternary it sits in has type double: the sum is formed in double
-          const double cand = static_cast<double>(pieces_[ret].score) + static_cast<double>(till_here);
+          const double cand = static_cast<double>(score_[ret]) + static_cast<double>(till_here);
           better = target.starts_at == -1 || cand > static_cast<double>(target.score);
           stored = static_cast<float>(cand);
         }
@@ -682,10 +726,11 @@ class Processor {
       ends_at = n.starts_at;
     }
     std::reverse(results.begin(), results.end());
-    return results;
   }
 
   std::vector<Piece> pieces_;
+  std::vector<float> score_;   // pieces_[i].score / .type once more, packed for the Viterbi loop
+  std::vector<uint8_t> type_;
   std::unordered_map<std::string, int> ids_;
   ByteTrie trie_, user_;
   int unk_id_ = -1;
@@ -711,25 +756,23 @@ class Vocabulary {
 
   // Vocabulary.cc:35-79: word ids of `line` and, for each, the bytes of `line` it came from (views INTO line)
   std::tuple<Words, Views> encode(const std::string_view &line, bool add_eos = false) const {
-    const auto spans = processor_.encode(line);
     Words words;
+    thread_local std::vector<std::pair<size_t, size_t>> ranges;
+    processor_.encode(line, &words, &ranges);
     Views views;
-    words.reserve(spans.size() + (add_eos ? 1 : 0)), views.reserve(spans.size());
-    for (const auto &s : spans) {
-      words.push_back(static_cast<Word>(s.id));
-      views.push_back(line.substr(s.begin, s.end - s.begin));
-    }
+    views.reserve(ranges.size());
+    for (const auto &[b, e] : ranges) views.push_back(line.substr(b, e - b));
     if (add_eos) words.push_back(eos_id());
     return {std::move(words), std::move(views)};
   }
   // Vocabulary.cc:81-104: the text of `words` in `decoded` and one view into it per word; with ignore_eos the last
   // view (the EOS the decoder closed the sentence with) is dropped
   Views decode(const Words &words, std::string &decoded, bool ignore_eos = true) const {
-    std::vector<int> ids(words.begin(), words.end());
-    std::vector<spm::Processor::Span> spans;
+    thread_local std::vector<std::pair<size_t, size_t>> ranges;
     Views views;
-    if (!processor_.decode(ids, &decoded, &spans)) spans.clear();
-    for (const auto &s : spans) views.emplace_back(decoded.data() + s.begin, s.end - s.begin);
+    processor_.decode(words, &decoded, &ranges);  // (an id outside the vocabulary: empty text, no views)
+    views.reserve(ranges.size());
+    for (const auto &[b, e] : ranges) views.emplace_back(decoded.data() + b, e - b);
     if (ignore_eos && !views.empty()) views.pop_back();
     return views;
   }

@@ -18,7 +18,11 @@
 //   respond <mode> <wrap_length> <hex text> <ids,ids;ids,...>   Request::complete  -> source annotation | target text + annotation
 //   pivot <mode> <wrap_length> <hex text> <targets of model 1> <targets of model 2>   process(AnnotatedText&) + combine
 //   recode <mode> <wrap_length> <hex text>     AnnotatedText::to(UTF8) and back -> both offset tables
+//   bench <mode> <wrap_length> <file> <reps>   timing: TextProcessor::process of the file's text, then Vocabulary::decode of
+//                                              every segment (the two host-side halves of a request) -> counts and seconds
+#include <chrono>
 #include <cstdio>
+#include <fstream>
 #include <iostream>
 #include <memory>
 #include <optional>
@@ -228,6 +232,31 @@ int main() {
           }
         }
       }
+    } else if (cmd == "bench") {
+      std::string mode, path;
+      size_t wrap = 0, reps = 1;
+      in >> mode >> wrap >> path >> reps;
+      std::ifstream f(path, std::ios::binary);
+      const std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+      auto processor = make_processor(mode, *vocabulary);
+      size_t sentences = 0, tokens = 0, decoded_bytes = 0;
+      double t_process = 0, t_decode = 0;
+      for (size_t r = 0; r < reps; r++) {
+        auto t0 = std::chrono::steady_clock::now();
+        auto [annotated, segments] = processor->process(std::string(text), wrap);
+        auto t1 = std::chrono::steady_clock::now();
+        for (const Segment &s : segments) {
+          std::string decoded;
+          Views views = vocabulary->decode(s, decoded, /*ignore_eos=*/false);
+          decoded_bytes += decoded.size() + views.size();
+        }
+        auto t2 = std::chrono::steady_clock::now();
+        t_process += std::chrono::duration<double>(t1 - t0).count(), t_decode += std::chrono::duration<double>(t2 - t1).count();
+        sentences += segments.size();
+        for (const Segment &s : segments) tokens += s.size();
+      }
+      out << "bench bytes=" << text.size() * reps << " sentences=" << sentences << " tokens=" << tokens << " process_s=" << t_process
+          << " decode_s=" << t_decode << " check=" << decoded_bytes;
     } else if (cmd.empty()) {
       continue;
     } else {
