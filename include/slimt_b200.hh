@@ -627,13 +627,14 @@ class Blocking {
     // the decoded text needs every history's alignment only when asked for; the words always
     const Histories histories = serve(model, pool, options);
     std::vector<Response> responses(annotated.size());
-    size_t at = 0;
-    for (size_t i = 0; i < annotated.size(); i++) {
-      Histories mine(histories.begin() + at, histories.begin() + at + segments[i].size());
-      at += segments[i].size();
+    std::vector<size_t> first(annotated.size() + 1, 0);
+    for (size_t i = 0; i < annotated.size(); i++) first[i + 1] = first[i] + segments[i].size();
+    // detokenisation and Response building per request: independent, on the same host threads as the tokenisation
+    parallel_for(annotated.size(), [&](size_t i) {
+      Histories mine(histories.begin() + first[i], histories.begin() + first[i + 1]);
       responses[i] = make_response(std::move(annotated[i]), mine, model->vocabulary());
       if (!options.alignment) responses[i].alignments.clear();
-    }
+    });
     return responses;
   }
 
