@@ -257,6 +257,43 @@ int main() {
       }
       out << "bench bytes=" << text.size() * reps << " sentences=" << sentences << " tokens=" << tokens << " process_s=" << t_process
           << " decode_s=" << t_decode << " check=" << decoded_bytes;
+#ifndef SLIMT_TEXT_REFERENCE
+    } else if (cmd == "loadfuzz") {
+      // product only: damaged vocabulary files must end in std::runtime_error (or load), never in a crash
+      std::string path;
+      uint64_t seed = 1;
+      size_t n = 0;
+      in >> path >> seed >> n;
+      std::ifstream f(path, std::ios::binary);
+      const std::string good((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+      size_t loaded = 0, refused = 0;
+      auto next = [&seed]() {
+        seed = seed * 6364136223846793005ULL + 1442695040888963407ULL;
+        return seed >> 33;
+      };
+      for (size_t k = 0; k < n; k++) {
+        std::string bad = good;
+        const int kind = static_cast<int>(next() % 4);
+        if (kind == 0) bad.resize(next() % (bad.size() + 1));                                   // truncated
+        if (kind == 1) for (int j = 0; j < 8; j++) bad[next() % bad.size()] = static_cast<char>(next());  // flipped bytes
+        if (kind == 2) bad.insert(next() % bad.size(), std::string(next() % 64, static_cast<char>(next())));  // inserted run
+        if (kind == 3) for (int j = 0; j < 64; j++) bad[(good.size() - 300000 + next() % 290000) % bad.size()] = static_cast<char>(next());  // charsmap / trie damage
+        try {
+          Vocabulary v(View{bad.data(), bad.size()});
+          auto [w, r] = v.encode("Hello wor\xef\xbc\xa1ld \xef\xac\x81ne. 12", true);
+          std::string text;
+          v.decode(w, text, false);
+          loaded++;
+        } catch (const std::runtime_error &) {
+          refused++;
+        } catch (const std::length_error &) {
+          refused++;
+        } catch (const std::bad_alloc &) {
+          refused++;
+        }
+      }
+      out << "loadfuzz loaded=" << loaded << " refused=" << refused;
+#endif
     } else if (cmd.empty()) {
       continue;
     } else {

@@ -121,3 +121,13 @@ def test_live_against_the_reference_build(driver):
         cmds.append(f"recode {mode} 128 {_hx(text)}")
         cmds.append(f"encode {_hx(_random_text(rng))}")
     assert _run(driver, cmds) == _run(REF_BIN, cmds)
+
+
+def test_damaged_vocabulary_files_are_refused_not_crashed_on(driver):
+    """Truncated, bit-flipped and spliced sentencepiece files (incl. damage inside the precompiled character map and its
+    double-array trie): the loader either throws or yields a vocabulary that still encodes and decodes; the process
+    survives (clean under -fsanitize=address,undefined as well)."""
+    out = _run(driver, ["loadfuzz tests/golden/text/spm_unigram.model 7 300", "loadfuzz tests/golden/text/spm_bytes.model 9 300"])
+    for line in out:
+        got = dict(kv.split("=") for kv in line.split()[1:])
+        assert int(got["loaded"]) + int(got["refused"]) == 300 and int(got["refused"]) > 100
