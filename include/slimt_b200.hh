@@ -32,6 +32,7 @@
 #include <future>
 #include <memory>
 #include <mutex>
+#include <optional>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -247,6 +248,68 @@ class MmapFile {
 };
 }  // namespace io
 
+// ---------------------------------------------------------------- Shortlist / ShortlistGenerator (slimt/Shortlist.hh)
+class Shortlist {  // Shortlist.hh:14-33: the sorted candidate word ids of one batch
+ public:
+  explicit Shortlist(Words words) : words_(std::move(words)) {}
+  const std::vector<Word> &words() const { return words_; }
+  Word reverse_map(int idx) const { return words_[idx]; }
+  int try_forward_map(Word w) const {
+    auto first = std::lower_bound(words_.begin(), words_.end(), w);
+    return (first != words_.end() && *first == w) ? static_cast<int>(std::distance(words_.begin(), first)) : -1;
+  }
+
+ private:
+  std::vector<Word> words_;
+};
+
+// Shortlist.hh:35-76 over the host-only C-ABI calls (no GPU needed): the binary lex.s2t.bin image stays the caller's
+// (a View, as in the reference); `vocabulary_size` is the target vocabulary's size, which bounds the candidate ids.
+// check = true runs the reference's header / size / checksum / content_check (Shortlist.cc:16-37, 68-98) at
+// construction and throws where the reference aborts.
+class ShortlistGenerator {
+ public:
+  ShortlistGenerator(View view, size_t vocabulary_size, bool check = false) : view_(view), vocab_(vocabulary_size) {
+    if (check) detail::check(slimt_b200_shortlist_check(view_.data, view_.size, vocab_), "ShortlistGenerator: check failed");
+  }
+  ShortlistGenerator(View view, const Vocabulary & /*source*/, const Vocabulary &target, size_t /*source_index*/ = 0,
+                     size_t /*target_index*/ = 1, bool /*shared*/ = false, bool check = false)
+      : ShortlistGenerator(view, target.size(), check) {}
+  // Shortlist.cc:115-175: first `frequent` ids + the targets of every distinct source word, padded to a multiple of 8
+  Shortlist generate(const Words &words) const {
+    Words out(vocab_ + 8);
+    size_t n = 0;
+    detail::check(slimt_b200_shortlist_generate(view_.data, view_.size, words.data(), words.size(), vocab_, out.data(), out.size(), &n),
+                  "slimt_b200_shortlist_generate");
+    out.resize(n);
+    return Shortlist(std::move(out));
+  }
+
+ private:
+  View view_;
+  size_t vocab_;
+};
+
+// Batcher::generate (Batcher.cc:95-120) as a plan over sentence lengths: batches in ascending length, each as many
+// sentences as fit `(n + 1) * longest <= max_words`.  The services run the same planner inside the C-ABI call.
+struct BatchPlan {
+  std::vector<size_t> ids;  // sentence indices of the batch
+  size_t width = 0;         // padded length
+};
+inline std::vector<BatchPlan> plan_batches(const Sentences &sentences, size_t max_words) {
+  std::vector<uint64_t> lengths(sentences.size()), ids(sentences.size()), offsets(sentences.size() + 1), widths(sentences.size() + 1);
+  for (size_t i = 0; i < sentences.size(); i++) lengths[i] = sentences[i].size();
+  size_t n = 0;
+  detail::check(slimt_b200_batcher_plan(lengths.data(), lengths.size(), max_words, ids.data(), offsets.data(), widths.data(), &n),
+                "slimt_b200_batcher_plan");
+  std::vector<BatchPlan> plan(n);
+  for (size_t b = 0; b < n; b++) {
+    plan[b].ids.assign(ids.begin() + offsets[b], ids.begin() + offsets[b + 1]);
+    plan[b].width = widths[b];
+  }
+  return plan;
+}
+
 // ---------------------------------------------------------------- Model (slimt/Model.hh)
 template <class Field>
 struct Package {
@@ -348,14 +411,7 @@ class Model {
     const size_t B = input.index(), T = input.indices().dim(-1);
     std::vector<uint32_t> lengths(input.lengths().begin(), input.lengths().end());
     std::vector<uint32_t> shortlist;
-    if (!shortlist_.empty()) {
-      shortlist.resize(vocab_ + 8);
-      size_t n = 0;
-      detail::check(slimt_b200_shortlist_generate(shortlist_.data(), shortlist_.size(), input.words().data(),
-                                                  input.words().size(), vocab_, shortlist.data(), shortlist.size(), &n),
-                    "slimt_b200_shortlist_generate");
-      shortlist.resize(n);
-    }
+    if (auto generator = shortlist_generator()) shortlist = generator->generate(input.words()).words();  // Model.cc:116-120
     // the first decoder step is unconditional (Model.cc:145-157): at least one step
     const size_t max_steps = std::max<size_t>(1, static_cast<size_t>(input.limit_factor() * static_cast<float>(T)));
     std::vector<uint32_t> steps(max_steps * std::max<size_t>(1, B));
@@ -393,6 +449,12 @@ class Model {
     return *processor_;
   }
   size_t id() const { return id_; }  // Model.hh:62
+  // Model.hh:63-65: absent when the package has no shortlist.  The candidate ids are bounded by the vocabulary's size
+  // when there is one (Shortlist.cc:116-117), else by the embedding's rows.
+  std::optional<ShortlistGenerator> shortlist_generator() const {
+    if (shortlist_.empty()) return std::nullopt;
+    return ShortlistGenerator(View{const_cast<char *>(shortlist_.data()), shortlist_.size()}, vocabulary_ ? vocabulary_->size() : vocab_);
+  }
   size_t vocabulary_size() const { return vocab_; }
   const std::vector<int> &devices() const { return devices_; }
   slimt_b200_model *handle() const { return replicas_[0]; }

@@ -33,5 +33,34 @@ int main(int argc, char **argv) {
   ok = ok && !cache.find(5).first && cache.find(13).first && cache.find(13).second == 130 && cache.find(6).first;
   std::printf("cache %s\n", ok ? "ok" : "BAD");
   std::printf("make_cache %d %d\n", slimt::make_cache(0) == nullptr, slimt::make_cache(16) != nullptr);
+
+  // optional: ShortlistGenerator / Shortlist (Shortlist.hh) and the batch plan on a shortlist file -- argv[3] = lex.s2t.bin,
+  // argv[4] = vocabulary size; the source words are 1..length
+  if (argc >= 5) {
+    slimt::io::MmapFile file(argv[3]);
+    const size_t vocab = std::strtoul(argv[4], nullptr, 10);
+    slimt::ShortlistGenerator generator(slimt::View{file.data(), file.size()}, vocab, /*check=*/true);
+    slimt::Shortlist shortlist = generator.generate(sentence);
+    std::printf("shortlist");
+    for (auto w : shortlist.words()) std::printf(" %u", w);
+    std::printf("\n");
+    const slimt::Word probe = shortlist.words()[shortlist.words().size() / 2];
+    std::printf("maps %d %d %u\n", shortlist.try_forward_map(probe), shortlist.try_forward_map(static_cast<slimt::Word>(vocab + 5)),
+                shortlist.reverse_map(static_cast<int>(shortlist.words().size() / 2)));
+    slimt::Sentences mixed;
+    for (size_t i = 0; i < 10; i++) mixed.push_back(slimt::Words((i * 7) % 11 + 1, 1));
+    for (const slimt::BatchPlan &b : slimt::plan_batches(mixed, 24)) {
+      std::printf("batch %zu:", b.width);
+      for (size_t id : b.ids) std::printf(" %zu", id);
+      std::printf("\n");
+    }
+    bool refused = false;
+    try {
+      slimt::ShortlistGenerator bad(slimt::View{file.data(), file.size() - 8}, vocab, /*check=*/true);
+    } catch (const std::runtime_error &) {
+      refused = true;
+    }
+    std::printf("truncated %s\n", refused ? "refused" : "accepted");
+  }
   return ok ? 0 : 1;
 }

@@ -149,3 +149,28 @@ def test_host_layer_matches_ctypes_path(gpu_ctx, tiny_model, shortlist_assets, t
     second, _ = m.translate(outs, max_words=96, shortlist_bin=sl_bin)
     assert a3 == [o.tolist() for o in second]
     m.close()
+
+
+def test_host_shortlist_generator_and_batch_plan(tmp_path):
+    """slimt::ShortlistGenerator / Shortlist (Shortlist.hh:14-76) and plan_batches (Batcher.cc:95-120) of the C++ layer
+    against the oracle's restatements; CPU only."""
+    from oracle import slimt_oracle as so
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "slimt_b200", "csrc"), "host_logic"])
+    fr, offs, lists = synth.make_shortlist(vocab=200, frequent=10, best=3, seed=5)
+    sl_path = str(tmp_path / "lex.bin")
+    synth.write_shortlist(sl_path, fr, offs, lists, best=3, checksum=True)  # check = true wants a real checksum
+    out = subprocess.run([LOGIC, "9", "128", sl_path, "200"], capture_output=True, text=True, check=True).stdout.split("\n")
+    got = list(map(int, next(l for l in out if l.startswith("shortlist")).split()[1:]))
+    want = so.shortlist_generate(np.array(list(range(1, 10)) + [0], dtype=np.uint32), fr, offs, lists, 200)
+    assert got == list(map(int, want)) and len(got) % 8 == 0
+    maps = next(l for l in out if l.startswith("maps")).split()
+    assert int(maps[1]) == len(got) // 2 and int(maps[2]) == -1 and int(maps[3]) == got[len(got) // 2]
+    # Batcher::generate: ascending length, (n + 1) * longest <= max_words
+    lengths = [(i * 7) % 11 + 1 for i in range(10)]
+    plan = [(int(l.split(":")[0].split()[1]), list(map(int, l.split(":")[1].split()))) for l in out if l.startswith("batch")]
+    seen = []
+    for width, ids in plan:
+        assert width == max(lengths[i] for i in ids) and len(ids) * width <= 24
+        seen += ids
+    assert sorted(seen) == list(range(10)) and [lengths[i] for i in seen] == sorted(lengths)
+    assert "truncated refused" in out
