@@ -108,9 +108,13 @@ int main(int argc, char **argv) {
     {
       auto two = std::make_shared<slimt::Model>(slimt::preset::tiny(), paths, std::vector<int>{0, 0});
       config.workers = 2;
-      slimt::Async async(config);
+      slimt::Config uncached = config;  // (a cached answer comes from whatever batch first produced it; section 5 tests the cache)
+      uncached.cache_size = 0;
+      slimt::Async async(uncached);
       std::future<slimt::WordsResponse> f1 = async.translate(two, sources);
-      std::future<slimt::WordsResponse> f2 = async.translate(two, slimt::Sentences(sources.begin(), sources.begin() + 1));
+      // (different options: requests of the same kind that wait together are pooled into one service call -- AggregateBatcher
+      // semantics -- and a pooled batch has a different shortlist union; this test compares each request served alone)
+      std::future<slimt::WordsResponse> f2 = async.translate(two, slimt::Sentences(sources.begin(), sources.begin() + 1), with_alignment);
       std::future<slimt::WordsResponse> f3 = async.pivot(two, model, sources, with_alignment);
       std::future<slimt::WordsResponse> f4 = async.translate(model, sources);  // a second model on the same device, concurrently
       put_sentences(out, f1.get().target);
