@@ -747,8 +747,8 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
   long long* trace_buf = nullptr;
   const size_t trace_n = static_cast<size_t>(c.num_sms) * kTraceSlots;
   if (trace_path) {
-    SB_CUDA(cudaMallocManaged(&trace_buf, 4 * trace_n * sizeof(long long)));
-    SB_CUDA(cudaMemsetAsync(trace_buf, 0, 4 * trace_n * sizeof(long long), s));
+    SB_CUDA(cudaMallocManaged(&trace_buf, 5 * trace_n * sizeof(long long)));
+    SB_CUDA(cudaMemsetAsync(trace_buf, 0, 5 * trace_n * sizeof(long long), s));
   }
 
   // ---- embedding (Model.cc:195-197)
@@ -1144,7 +1144,8 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
       const double Md = B, Nd = Nout, Kd = E;
       LaunchScope ls(c, "dec_gemm_out_argmax", 2.0 * Md * Nd * Kd, Md * Kd + Nd * Kd + 4.0 * Nd + 8.0 * Md);
       const int rc = out_ext ? launch_gemm_out_argmax_ext(map_oq, map_wout, map_ext, pb_out, dshift_out, m.out.um, c.fast, B,
-                                                          Nout, E, best, c.num_sms, s)
+                                                          Nout, E, best, c.num_sms, s,
+                                                          (trace_buf && step == 3) ? trace_buf + 4 * trace_n : nullptr)
                              : launch_gemm_out_argmax(map_oq, map_wout, pb_out, c127_out, dmax_out,
                                                       c.fast ? ipb6_out : nullptr, m.out.um, m.out.eta, B, Nout, E, best,
                                                       c.num_sms, s);
@@ -1191,12 +1192,13 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
   if (trace_buf) {
     SB_CUDA(cudaStreamSynchronize(s));
     if (FILE* f = fopen(trace_path, "w")) {
-      for (int k = 0; k < 4; k++)
+      for (int k = 0; k < 5; k++)
         for (int cta = 0; cta < c.num_sms; cta++) {
           const long long* t = trace_buf + k * trace_n + static_cast<size_t>(cta) * kTraceSlots;
           if (t[0] == 0) continue;
-          fprintf(f, "%s %d", k == 0 ? "ssru" : k == 1 ? "ffn" : k == 2 ? "encffn" : "cross", cta);
-          for (int i = 0; i < kTraceSlots; i++) fprintf(f, " %lld", t[i] ? t[i] - t[0] : -1);
+          fprintf(f, "%s %d", k == 0 ? "ssru" : k == 1 ? "ffn" : k == 2 ? "encffn" : k == 3 ? "cross" : "out", cta);
+          // (the output GEMM's slots 4.. are counts and accumulated waits, not stamps)
+          for (int i = 0; i < kTraceSlots; i++) fprintf(f, " %lld", (k == 4 && i >= 4) ? t[i] : (t[i] ? t[i] - t[0] : -1));
           fprintf(f, "\n");
         }
       fclose(f);

@@ -82,6 +82,6 @@ int launch_gemm_out_argmax(const CUtensorMap& tma_a, const CUtensorMap& tma_b, c
 // maximum of the float logits.
 int launch_gemm_out_argmax_ext(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const CUtensorMap& tma_e, const float* pb,
                                const int32_t* dshift, float um, bool fast, int M, int N, int K, unsigned long long* best,
-                               int num_sms, cudaStream_t stream);
+                               int num_sms, cudaStream_t stream, long long* trace = nullptr);
 
 }  // namespace sb

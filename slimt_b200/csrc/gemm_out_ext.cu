@@ -56,12 +56,12 @@ __device__ __forceinline__ unsigned long long pack_float_key(float v, uint32_t i
   return (static_cast<unsigned long long>(key) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - idx);
 }
 
-template <int KB, bool kFast>
+template <int KB, bool kFast, bool kTrace>
 __global__ void __launch_bounds__(kThreadsX, 1)
     out_argmax_ext_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                           const __grid_constant__ CUtensorMap tma_e, const float* __restrict__ pb,
                           const int32_t* __restrict__ dshift, float um, float inv_um, int M, int N,
-                          unsigned long long* __restrict__ best) {
+                          unsigned long long* __restrict__ best, long long* __restrict__ trace) {
   using L = ExtSmem<KB>;
   constexpr int kStages = L::kStages;
   constexpr int kABytes = kBM * kBK;
@@ -123,7 +123,14 @@ __global__ void __launch_bounds__(kThreadsX, 1)
   __syncthreads();
   tc_fence_after();
   pdl_launch_dependents();
+  // optional per-CTA profile (SLIMT_B200_TRACE): 0 entry, 1 released by the previous kernel, 2 last tile's epilogue done,
+  // 3 exit, 4 tiles, 5 weight tiles, 6-8 MMA thread waiting for weights / a free accumulator buffer / activation tiles,
+  // 9 strips that took the exact path (epilogue warp 4)
+  // (a template flag, not a run-time test: the test alone cost 3 us per launch in the single-thread MMA loop)
+  long long* tr = (kTrace && trace) ? trace + static_cast<size_t>(blockIdx.x) * 128 : nullptr;
+  if (kTrace && tr && threadIdx.x == 0) tr[0] = clock64();
   pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
+  if (kTrace && tr && threadIdx.x == 0) tr[1] = clock64(), tr[4] = t_end - t_begin;
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -160,21 +167,32 @@ __global__ void __launch_bounds__(kThreadsX, 1)
       const uint64_t dbe = make_kmajor_sw128_desc(smem_u32(smem_be));
       uint32_t kbc = 0, run = 0, i = 0;
       int n = n_first, m = m_first, cur_n = -1;
+      long long w_b = 0, w_t = 0, w_a = 0;
       for (int t = t_begin; t < t_end; t++, i++) {
         if (n != cur_n) {
+          const long long c0 = (kTrace && tr) ? clock64() : 0;
           mbar_wait(b_full, run & 1);
+          if (kTrace && tr) w_b += clock64() - c0;
           cur_n = n;
           run++;
         }
         const uint32_t buf = i & 1;
         const uint32_t tmem_d = tmem_base + buf * kBN;
-        mbar_wait(&tmem_empty[buf], ((i >> 1) & 1) ^ 1);
+        {
+          const long long c0 = (kTrace && tr) ? clock64() : 0;
+          mbar_wait(&tmem_empty[buf], ((i >> 1) & 1) ^ 1);
+          if (kTrace && tr) w_t += clock64() - c0;
+        }
         tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < KB; kb++, kbc++) {
           const uint32_t s = kbc % kStages;
           const uint32_t ph = (kbc / kStages) & 1;
-          mbar_wait(&full_bar[s], ph);
+          {
+            const long long c0 = (kTrace && tr) ? clock64() : 0;
+            mbar_wait(&full_bar[s], ph);
+            if (kTrace && tr) w_a += clock64() - c0;
+          }
           tc_fence_after();
           const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + s * kABytes));
           const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + kb * kBBytes));
@@ -188,6 +206,7 @@ __global__ void __launch_bounds__(kThreadsX, 1)
         if (last_of_run) umma_commit(b_empty);
         if (++m == m_tiles) m = 0, n++;
       }
+      if (kTrace && tr) tr[5] = run, tr[6] = w_b, tr[7] = w_t, tr[8] = w_a;
     }
   } else if (warp >= 4) {
     // ===== epilogue: thread <-> TMEM lane <-> output row; warp = (lane quadrant, 64-column strip) =====
@@ -265,6 +284,7 @@ __global__ void __launch_bounds__(kThreadsX, 1)
         thr = max(mx, floor_p) - kDelta;
       }
       if (__any_sync(0xffffffffu, trig)) {
+        if (kTrace && tr && warp == 4 && lane == 0) tr[9]++;
         int bi = -1;
         int bvi = INT_MIN;   // tolerance mode: best proxy
         float bvf = 0.0f;    // exact mode: best logit
@@ -300,18 +320,20 @@ __global__ void __launch_bounds__(kThreadsX, 1)
       }
       m = m_nx, n = n_nx;
     }
+    if (kTrace && tr && warp == 4 && lane == 0) tr[2] = clock64();
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<512>(tmem_base);
+  if (kTrace && tr && threadIdx.x == 0) tr[3] = clock64();
 }
 
 }  // namespace
 
 int launch_gemm_out_argmax_ext(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const CUtensorMap& tma_e, const float* pb,
                                const int32_t* dshift, float um, bool fast, int M, int N, int K, unsigned long long* best,
-                               int num_sms, cudaStream_t stream) {
+                               int num_sms, cudaStream_t stream, long long* trace) {
   const int KB = K / kBK;
   const long tiles = static_cast<long>((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
   const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
@@ -320,10 +342,11 @@ int launch_gemm_out_argmax_ext(const CUtensorMap& tma_a, const CUtensorMap& tma_
   auto go = [&](auto kern, size_t smem) {
     if (ensure_dyn_smem(kern, smem) != cudaSuccess) return 1;
     return launch_pdl(kern, dim3(grid), dim3(kThreadsX), smem, stream, tma_a, tma_b, tma_e, pb, dshift, um, inv_um, M, N,
-                      best) != cudaSuccess ? 1 : 0;
+                      best, trace) != cudaSuccess ? 1 : 0;
   };
-  if (KB == 2) return fast ? go(out_argmax_ext_kernel<2, true>, ExtSmem<2>::total) : go(out_argmax_ext_kernel<2, false>, ExtSmem<2>::total);
-  if (KB == 4) return fast ? go(out_argmax_ext_kernel<4, true>, ExtSmem<4>::total) : go(out_argmax_ext_kernel<4, false>, ExtSmem<4>::total);
+  if (trace != nullptr && KB == 2 && !fast) return go(out_argmax_ext_kernel<2, false, true>, ExtSmem<2>::total);  // the profiled build
+  if (KB == 2) return fast ? go(out_argmax_ext_kernel<2, true, false>, ExtSmem<2>::total) : go(out_argmax_ext_kernel<2, false, false>, ExtSmem<2>::total);
+  if (KB == 4) return fast ? go(out_argmax_ext_kernel<4, true, false>, ExtSmem<4>::total) : go(out_argmax_ext_kernel<4, false, false>, ExtSmem<4>::total);
   return 1;
 }
 

@@ -58,7 +58,7 @@ def main():
             os.environ["SLIMT_B200_TRACE"] = raw
         model.forward(tok, lens, shortlist=sl)
     os.environ.pop("SLIMT_B200_TRACE")
-    rows = {"ssru": [], "ffn": [], "encffn": [], "cross": []}
+    rows = {"ssru": [], "ffn": [], "encffn": [], "cross": [], "out": []}
     for line in open(raw):
         p = line.split()
         rows[p[0]].append([int(x) for x in p[2:]])
@@ -73,6 +73,24 @@ def main():
             for slot in sorted(names, key=lambda k: (med[k], k)):
                 if not np.isnan(med[slot]):
                     f.write(f"  {med[slot]:9.0f} [{lo[slot]:8.0f}, {hi[slot]:8.0f}]  {names[slot]}\n")
+        if rows["out"]:  # output GEMM: one line per CTA (stamps 1-3 since entry, then counts and accumulated waits)
+            a = np.array(rows["out"], dtype=np.int64)
+            f.write(f"== out: {len(a)} CTAs; per CTA: released, epilogue done, exit (cycles since entry) | tiles, weight tiles | "
+                    "MMA thread waited for weights, accumulator buffer, activations | exact-path strips (warp 4)\n")
+            busy = a[:, 3] - a[:, 1]
+            f.write(f"  busy (exit - released): min {busy.min()} median {int(np.median(busy))} max {busy.max()}\n")
+            for key, label in ((5, "weight tiles"), (4, "tiles")):
+                for v in sorted(set(a[:, key].tolist())):
+                    sel = a[:, key] == v
+                    f.write(f"  {label} = {v}: {int(sel.sum())} CTAs, busy median {int(np.median(busy[sel]))}, waits (weights, buffer, activations) "
+                            f"{int(np.median(a[sel, 6]))} {int(np.median(a[sel, 7]))} {int(np.median(a[sel, 8]))}, exact strips {int(np.median(a[sel, 9]))}\n")
+            f.write("  busy by CTA: " + " ".join(str(int(b) // 100) for b in busy) + "  (x100 cycles)\n")
+            f.write("  buffer waits by CTA: " + " ".join(str(int(b) // 100) for b in a[:, 7]) + "\n")
+            f.write("  exact strips by CTA: " + " ".join(str(int(b)) for b in a[:, 9]) + "\n")
+            order = np.argsort(busy)
+            for cta in list(order[:5]) + list(order[-8:]):
+                f.write("  cta %3d: released %6d epi %6d exit %6d | %2d tiles %d weight tiles | waits %6d %6d %6d | exact %3d\n" %
+                        (cta, a[cta, 1], a[cta, 2], a[cta, 3], a[cta, 4], a[cta, 5], a[cta, 6], a[cta, 7], a[cta, 8], a[cta, 9]))
     print(open(out_path).read())
 
 
