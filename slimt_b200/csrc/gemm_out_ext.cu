@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kThreadsX, 1)
   pdl_launch_dependents();
   // optional per-CTA profile (SLIMT_B200_TRACE): 0 entry, 1 released by the previous kernel, 2 last tile's epilogue done,
   // 3 exit, 4 tiles, 5 weight tiles, 6-8 MMA thread waiting for weights / a free accumulator buffer / activation tiles,
-  // 9 strips that took the exact path (epilogue warp 4)
+  // 9 strips that took the exact path, 10 eight-column groups evaluated exactly (all epilogue warps)
   // (a template flag, not a run-time test: the test alone cost 3 us per launch in the single-thread MMA loop)
   long long* tr = (kTrace && trace) ? trace + static_cast<size_t>(blockIdx.x) * 128 : nullptr;
   if (kTrace && tr && threadIdx.x == 0) tr[0] = clock64();
@@ -284,13 +284,14 @@ __global__ void __launch_bounds__(kThreadsX, 1)
         thr = max(mx, floor_p) - kDelta;
       }
       if (__any_sync(0xffffffffu, trig)) {
-        if (kTrace && tr && warp == 4 && lane == 0) tr[9]++;
+        if (kTrace && tr && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(tr + 9), 1ull);  // strips on the exact path, all warps
         int bi = -1;
         int bvi = INT_MIN;   // tolerance mode: best proxy
         float bvf = 0.0f;    // exact mode: best logit
 #pragma unroll
         for (int k = 0; k < 8; k++) {
           if (__any_sync(0xffffffffu, trig && g[k] >= thr)) {
+            if (kTrace && tr && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(tr + 10), 1ull);  // 8-column groups evaluated
 #pragma unroll
             for (int jj = 0; jj < 8; jj++) {
               const int j = 8 * k + jj;

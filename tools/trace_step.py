@@ -87,6 +87,8 @@ def main():
             f.write("  busy by CTA: " + " ".join(str(int(b) // 100) for b in busy) + "  (x100 cycles)\n")
             f.write("  buffer waits by CTA: " + " ".join(str(int(b) // 100) for b in a[:, 7]) + "\n")
             f.write("  exact strips by CTA: " + " ".join(str(int(b)) for b in a[:, 9]) + "\n")
+            f.write("  exact groups by CTA: " + " ".join(str(int(b)) for b in a[:, 10]) + "\n")
+            f.write("  correlation(busy, exact groups) = %.3f\n" % np.corrcoef(busy, a[:, 10])[0, 1])
             order = np.argsort(busy)
             for cta in list(order[:5]) + list(order[-8:]):
                 f.write("  cta %3d: released %6d epi %6d exit %6d | %2d tiles %d weight tiles | waits %6d %6d %6d | exact %3d\n" %
