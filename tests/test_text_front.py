@@ -131,3 +131,25 @@ def test_damaged_vocabulary_files_are_refused_not_crashed_on(driver):
     for line in out:
         got = dict(kv.split("=") for kv in line.split()[1:])
         assert int(got["loaded"]) + int(got["refused"]) == 300 and int(got["refused"]) > 100
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/slimt"), reason="the reference sources only exist in the build container")
+def test_live_against_the_reference_build_on_real_text(driver):
+    """Half a megabyte of real English prose with code, lists, quotes, abbreviations and numbers (the Python documentation
+    topics shipped with the interpreter) through the splitter in all three modes and through TextProcessor::process."""
+    topics = pytest.importorskip("pydoc_data.topics")
+    subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(ROOT, "oracle"), "text_ref"])
+    text = "\n\n".join(topics.topics.values())
+    chunks, cur = [], ""
+    for para in text.split("\n\n"):
+        cur += para + "\n\n"
+        if len(cur) > 3000:
+            chunks.append(cur)
+            cur = ""
+    cmds = ["vocab tests/golden/text/spm_unigram.model"]
+    for c in chunks:
+        for mode in ("wrapped_text", "paragraph", "sentence"):
+            cmds.append(f"split {mode} - {_hx(c)}")
+        cmds.append(f"process wrapped_text 64 {_hx(c)}")
+    assert len(cmds) > 400
+    assert _run(driver, cmds) == _run(REF_BIN, cmds)
