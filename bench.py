@@ -365,7 +365,7 @@ def workload_config():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=150,
+    ap.add_argument("--steps", type=int, default=200,
                     help="timed passes; the default keeps the timed region above 2 s at the headline size")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
