@@ -21,7 +21,7 @@ import make_text_golden as g  # noqa: E402
 TMP = "/tmp/slimt_b200_text_bench"
 
 
-def assets():
+def assets(n_lines=4096):
     import sentencepiece as spm
     os.makedirs(TMP, exist_ok=True)
     rng = random.Random(11)
@@ -43,7 +43,7 @@ def assets():
     text = os.path.join(TMP, "text.txt")
     rng = random.Random(12)
     lines, tokens = [], 0
-    while len(lines) < 4096:
+    while len(lines) < n_lines:
         s = line(rng.randint(20, 34))
         n = len(sp.encode(s)) + 1
         if 24 <= n <= 40:
@@ -62,9 +62,11 @@ def assets():
 
 def main():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "slimt_b200", "csrc"), "text_bench"])
-    model, vocab, sl, text, tokens = assets()
     devices = sys.argv[1] if len(sys.argv) > 1 else "0"
-    for workers in (1, 4, 8, 16):
+    n_gpus = len(devices.split(","))
+    # one GPU: one 4096-line batch, as the headline; N GPUs: two such batches per replica from ONE request
+    model, vocab, sl, text, tokens = assets(4096 if n_gpus == 1 else 4096 * 2 * n_gpus)
+    for workers in ((1, 4, 8, 16) if n_gpus == 1 else (4, 8, 16, 32)):
         r = subprocess.run([os.path.join(ROOT, "tools", "_bin", "text_bench"), model, vocab, sl, text, str(workers), "5", str(4096 * 40), devices],
                            capture_output=True, text=True)
         if r.returncode != 0:
@@ -75,7 +77,7 @@ def main():
         d["target_tokens_per_s_word_ids"] = round(d["target_tokens"] / d["words_s"])
         d["source_tokens_per_s_tokenize"] = round(d["source_tokens"] / d["tokenize_s"])
         d["host_share_of_e2e"] = round(1.0 - d["words_s"] / d["e2e_s"], 3)
-        d["workload"] = "tiny11 int8 + shortlist, 4096 lines of synthetic text (24-40 tokens each), 32000-piece unigram vocabulary, sentence mode"
+        d["workload"] = f"tiny11 int8 + shortlist, {d['sentences']} lines of synthetic text (24-40 tokens each), 32000-piece unigram vocabulary, sentence mode"
         print(json.dumps(d), flush=True)
     return 0
 
