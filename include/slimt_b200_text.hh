@@ -199,16 +199,25 @@ class ByteTrie {
       int k = first_[n];
       for (const auto &[c, to] : kids[n]) label_[k] = c, child_[k] = to, k++;
     }
-    root_.fill(-1);  // the root has the most children and is visited once per character: a direct table
-    for (const auto &[c, to] : kids[0]) root_[c] = to;
+    // nodes with many children (the root, the node behind U+2581, ...) get a direct 256-entry table
+    dense_of_.assign(kids.size(), -1);
+    dense_.clear();
+    for (size_t n = 0; n < kids.size(); n++) {
+      if (n != 0 && kids[n].size() <= kDenseFrom) continue;
+      dense_of_[n] = static_cast<int>(dense_.size() / 256);
+      dense_.resize(dense_.size() + 256, -1);
+      for (const auto &[c, to] : kids[n]) dense_[dense_.size() - 256 + c] = to;
+    }
   }
   bool empty() const { return value_.size() <= 1; }
+  size_t dense_nodes() const { return dense_.size() / 256; }
   // one step from `node` along byte c: the child or -1
   int step(int node, uint8_t c) const {
-    if (node == 0) return root_[c];
-    const uint8_t *lo = label_.data() + first_[node], *hi = label_.data() + first_[node + 1];
-    const uint8_t *it = std::lower_bound(lo, hi, c);
-    return (it != hi && *it == c) ? child_[it - label_.data()] : -1;
+    const int d = dense_of_[node];
+    if (d >= 0) return dense_[static_cast<size_t>(d) * 256 + c];
+    for (int k = first_[node], e = first_[node + 1]; k < e; k++)  // at most kDenseFrom sorted labels
+      if (label_[k] >= c) return label_[k] == c ? child_[k] : -1;
+    return -1;
   }
   int value(int node) const { return value_[node]; }
   // length of the longest key that is a prefix of s (0: none)
@@ -224,9 +233,9 @@ class ByteTrie {
   }
 
  private:
-  std::vector<int> first_, child_, value_;
+  static constexpr size_t kDenseFrom = 6;
+  std::vector<int> first_, child_, value_, dense_of_, dense_;
   std::vector<uint8_t> label_;
-  std::array<int, 256> root_{};
 };
 
 // The slice of sentencepiece::SentencePieceProcessor that slimt::Vocabulary calls (Vocabulary.cc:24-104): Load /
@@ -377,6 +386,16 @@ class Processor {
     if (!whitespace_as_suffix_ && add_dummy_prefix_) add_ws();
     bool prev_space = remove_extra_whitespaces_;
     while (!input.empty()) {
+      // an ASCII byte that starts no rule and no user-defined symbol maps to itself: the common case, without the walk
+      const uint8_t c0 = static_cast<uint8_t>(input.front());
+      if (c0 != ' ' && plain_ascii_[c0]) {
+        normalized->push_back(static_cast<char>(c0));
+        norm_to_orig->push_back(static_cast<size_t>(consumed));
+        prev_space = false;
+        consumed += 1;
+        input.remove_prefix(1);
+        continue;
+      }
       const auto p = normalize_prefix(input);
       std::string_view sp = p.first;
       while (prev_space && !sp.empty() && sp.front() == ' ') sp.remove_prefix(1);
@@ -614,6 +633,15 @@ class Processor {
       std::memcpy(darts_.data(), charsmap_.data() + 4, trie_bytes);
       replacements_at_ = 4 + static_cast<size_t>(trie_bytes);
     }
+    // bytes below 0x80 for which NormalizePrefix is the identity: no rule of the character map and no user-defined
+    // symbol starts with them
+    for (int c = 0; c < 256; c++) {
+      const char ch = static_cast<char>(c);
+      size_t length = 0;
+      uint32_t value = 0;
+      plain_ascii_[c] = c < 0x80 && !darts_has_prefix(ch) && user_.step(0, static_cast<uint8_t>(c)) < 0 &&
+                        !darts_longest(std::string_view(&ch, 1), &length, &value);
+    }
   }
 
   // Darts::DoubleArray::commonPrefixSearch restricted to what NormalizePrefix keeps: the LONGEST key that is a prefix of
@@ -640,6 +668,15 @@ class Processor {
       }
     }
     return found;
+  }
+
+  // does any key of the character map start with byte c?
+  bool darts_has_prefix(char ch) const {
+    if (darts_.empty()) return false;
+    auto offset = [](uint32_t u) { return (u >> 10) << ((u & (1u << 9)) >> 6); };
+    const uint8_t c = static_cast<uint8_t>(ch);
+    size_t pos = offset(darts_[0]) ^ c;
+    return pos < darts_.size() && (darts_[pos] & ((1u << 31) | 0xFFu)) == c;
   }
 
   // Normalizer::NormalizePrefix (normalizer.cc:195-254): (replacement text, input bytes consumed)
@@ -729,6 +766,7 @@ class Processor {
   }
 
   std::vector<Piece> pieces_;
+  std::array<bool, 256> plain_ascii_{};
   std::vector<float> score_;   // pieces_[i].score / .type once more, packed for the Viterbi loop
   std::vector<uint8_t> type_;
   std::unordered_map<std::string, int> ids_;
