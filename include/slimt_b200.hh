@@ -23,6 +23,7 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
@@ -770,14 +771,38 @@ class Blocking {
   size_t cache_hits_ = 0;
 };
 
-// Handle (Response.hh:60-91): what Async returns for a text request -- the future of its Response
+// Types.hh:24-27
+struct Fraction {
+  size_t p = 0;
+  size_t q = 0;
+};
+
+// Handle (Response.hh:60-91): what Async returns for a text request -- the future of its Response.  info() has the
+// reference's shape; a request is served by one C-ABI call here, so only `parts` moves (0 / n until the answer is there,
+// then n / n; a pivot has two parts) and the word / segment counters stay 0 / 0: they are in the Response.
 class Handle {
  public:
-  explicit Handle(std::future<Response> &&future) : future_(std::move(future)) {}
+  Handle(std::future<Response> &&future, size_t parts, size_t words, size_t segments)
+      : future_(std::move(future)), parts_(parts), words_(words), segments_(segments), start_(std::chrono::steady_clock::now()) {}
+  explicit Handle(std::future<Response> &&future) : Handle(std::move(future), 1, 0, 0) {}
+  struct Info {
+    double wps;
+    Fraction parts;
+    Fraction words;
+    Fraction segments;
+  };
+  Info info() {
+    const bool done = future_.valid() && future_.wait_for(std::chrono::seconds(0)) == std::future_status::ready;
+    const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - start_).count();
+    return Info{done && elapsed > 0 ? static_cast<double>(words_) / elapsed : 0.0, Fraction{done ? parts_ : 0, parts_},
+                Fraction{done ? words_ : 0, words_}, Fraction{done ? segments_ : 0, segments_}};
+  }
   std::future<Response> &future() { return future_; }
 
  private:
   std::future<Response> future_;
+  size_t parts_, words_, segments_;
+  std::chrono::steady_clock::time_point start_;
 };
 
 // Async (Frontend.hh:59-78, Frontend.cc:207-323): `workers` threads take requests from one queue and answer through
@@ -799,13 +824,13 @@ class Async {
   // ---- text level (Frontend.cc:229-314)
   Handle translate(const Ptr<Model> &model, std::string source, const Options &options = Options()) {
     Job job{model, nullptr, {}, options, {}, true, std::move(source), {}};
-    Handle handle(job.text_promise.get_future());
+    Handle handle(job.text_promise.get_future(), /*parts=*/1, 0, 0);
     enqueue(std::move(job));
     return handle;
   }
   Handle pivot(const Ptr<Model> &first, const Ptr<Model> &second, std::string source, const Options &options = Options()) {
     Job job{first, second, {}, options, {}, true, std::move(source), {}};
-    Handle handle(job.text_promise.get_future());
+    Handle handle(job.text_promise.get_future(), /*parts=*/2, 0, 0);
     enqueue(std::move(job));
     return handle;
   }

@@ -96,7 +96,10 @@ int main(int argc, char **argv) {
     print("async", a1);
     print("cached", a2);
     Handle h3 = async.pivot(model, model, sources[0], options);
-    print("apivot", h3.future().get());
+    const Handle::Info before = h3.info();
+    Response pivoted_async = h3.future().get();
+    print("apivot", pivoted_async);
+    std::cout << "info parts " << before.parts.q << "\n";
     // a burst of single-line requests: the requests that queue up while the first is served share one service call
     // (AggregateBatcher, Batcher.hh:128-200); each answer is compared with the same text served alone
     {
