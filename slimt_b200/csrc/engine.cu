@@ -885,8 +885,12 @@ int model_forward_on(Model& m, Context& c, ForwardArgs& a) {
 
   // ---- cross-attention K/V.  The reference re-projects them every step (Modules.cc:244-249); so does the
   // recompute kernel (tensor cores, from the u8 encoder output); otherwise they are projected once and cached.
+  // Small batches take the cached kernel: below ~4 k source tokens the recompute kernel has fewer sentence groups than
+  // SMs and its launch is all latency (64 x 32: 8.6 us cached against 12.8 us recomputed per launch, 5.40 -> 5.13 ms per
+  // batch; the two are bit-identical).  SLIMT_B200_CROSS = cached | rc overrides the choice (tests, A/B runs).
   const char* ca_env = getenv("SLIMT_B200_CROSS");
-  const bool ca_cached = ca_env && strcmp(ca_env, "cached") == 0;
+  const bool ca_force_rc = ca_env && strcmp(ca_env, "rc") == 0;
+  const bool ca_cached = (ca_env && strcmp(ca_env, "cached") == 0) || (!ca_force_rc && static_cast<long>(B) * T <= 4096);
   // long sentences (65 .. 256 tokens) take the sentence-at-a-time recompute kernel (cross_attention_rcl.cu; bit-exact mode)
   const bool cross_rcl = !ca_cached && !c.fast && !cross_attention_rc_supported(E, H, dh, T) && cross_attention_rcl_supported(E, H, dh, T);
   const bool cross_rc = cross_rcl || (cross_attention_rc_supported(E, H, dh, T) && !ca_cached);

@@ -80,6 +80,7 @@ def test_cross_attention_recompute_equals_cached_path(tiny_gpu, shape, monkeypat
     sents[-1] = synth.make_sentences(1, T, seed=3)[0]
     tokens, lengths = util.pad_batch(sents)
     ref = orc.forward(tokens, lengths, keep=True)
+    monkeypatch.setenv("SLIMT_B200_CROSS", "rc")  # (small batches would take the cached kernel by themselves)
     rc = m.forward(tokens, lengths, want_logits=True, want_alignment=True)
     monkeypatch.setenv("SLIMT_B200_CROSS", "cached")
     cached = m.forward(tokens, lengths, want_logits=True, want_alignment=True)
@@ -102,6 +103,7 @@ def test_long_sentence_cross_attention_recompute_equals_cached_path(tiny_gpu, sh
     sents[-1] = synth.make_sentences(1, max(1, T - 3), seed=3)[0]
     tokens, lengths = util.pad_batch(sents)
     lf = 0.25 if B * T <= 1024 else 0.1
+    monkeypatch.setenv("SLIMT_B200_CROSS", "rc")
     rc = m.forward(tokens, lengths, want_logits=True, want_alignment=True, limit_factor=lf)
     monkeypatch.setenv("SLIMT_B200_CROSS", "cached")
     cached = m.forward(tokens, lengths, want_logits=True, want_alignment=True, limit_factor=lf)
