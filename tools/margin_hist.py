@@ -9,7 +9,7 @@ with the per-step logits tap, exact mode and tolerance mode, and prints one JSON
   how input-dependent the outputs are (distinct tokens, distinct sentences);
   tolerance-mode agreement on the same decisions (teacher-forced by construction: both modes see their own history,
   so only the first divergence per sentence is counted as a flipped decision).
-usage (GPU box): python tools/margin_hist.py [N] > profiles/<tag>_margin_histogram.json"""
+usage (GPU box): python tools/margin_hist.py [N] > profiles/<tag>_margin_histogram.json      (CPU only: add --oracle)"""
 import json
 import os
 import sys
@@ -41,8 +41,39 @@ def margins(out, lengths):
     return rel, alive
 
 
+def oracle_main(n):
+    """The same histogram from the CPU oracle (bit-identical logits, tests/test_gpu_model.py): no GPU needed, no
+    tolerance-mode part."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import slimt_oracle as so
+    from slimt_b200 import synth
+    import sb_testutil as util
+    tmp = tempfile.mkdtemp(prefix="slimt_b200_margin_")
+    model_path, _, _, sentences = bench.build_assets(tmp, 0)
+    tokens, lengths = util.pad_batch(sentences[:n])
+    ref = so.Oracle(synth.read_model(model_path)).forward(tokens, lengths, keep=True)
+    out = {"steps": len(ref["step_tokens"]), "logits": ref["logits"], "step_tokens": np.asarray(ref["step_tokens"])}
+    rel, alive = margins(out, lengths)
+    r = rel[alive]
+    edges = [0.0, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1, 1.0, np.inf]
+    toks = out["step_tokens"]
+    report = {"workload": f"first {n} sentences of the headline batch (tiny11 random-init seed {bench.MODEL_SEED}), full vocabulary; CPU oracle",
+              "edges_relative_margin": [str(e) for e in edges], "decisions": int(alive.sum()),
+              "histogram": np.histogram(r, bins=edges)[0].tolist(),
+              "quantiles": {q: float(np.quantile(r, float(q))) for q in ("0.001", "0.01", "0.1", "0.5", "0.9")},
+              "share_below_rtol_1e-3": float((r < 1e-3).mean()), "exact_ties": int((r == 0).sum()),
+              "distinct_tokens": int(len(np.unique(toks[alive]))),
+              "distinct_sentences": int(len({tuple(toks[:, b].tolist()) for b in range(n)})),
+              "sentences_reaching_eos": int(sum(1 for b in range(n) if (toks[:, b] == 0).any()))}
+    for m in (1e-3, 1e-4, 1e-5):
+        report[f"sentences_with_every_margin_above_{m:g}"] = float(np.mean([(rel[alive[:, b], b] >= m).all() for b in range(n)]))
+    print(json.dumps(report))
+
+
 def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+    n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 128
+    if "--oracle" in sys.argv:
+        return oracle_main(n)
     ctx = capi.Context(0)
     tmp = tempfile.mkdtemp(prefix="slimt_b200_margin_")
     model_path, sl_path, shortlist, sentences = bench.build_assets(tmp, 0)
