@@ -64,6 +64,8 @@ WORKLOADS = {
                        "(BASELINE.json configs[4], per-step slice of the 1M-sentence sweep)"),
 }
 WL = WORKLOADS["tiny_shortlist"]
+# exploration only: SLIMT_B200_BENCH_MAX_WORDS overrides the workload's Batcher limit (the chosen values stay in the table)
+_MW = os.environ.get("SLIMT_B200_BENCH_MAX_WORDS")
 
 
 def wl_dims():
@@ -383,7 +385,10 @@ def main():
                     help="bracket the timed steps with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
     global WL
-    WL = WORKLOADS[args.workload]
+    WL = dict(WORKLOADS[args.workload])
+    if _MW:
+        WL["max_words"] = int(_MW)
+        WL["desc"] += f" [max_words overridden to {_MW}]"
     if args.impl == "reference":
         return run_reference_arm(args)
     if args.single_process:
